@@ -1,0 +1,95 @@
+"""ctypes front-end of oracle/liboracle.so (the CPU restatement of the path).
+
+TEST INFRASTRUCTURE ONLY: may be imported by tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs, never by the product
+package kaldi_ctc_b200.  See the headers of ctc_oracle.c / rnn_oracle.c for
+what is restated and how it is pinned.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = ctypes.CDLL(path)
+        for name in ("rnn_oracle_param_count_f32", "rnn_oracle_param_count_f64",
+                     "rnn_oracle_locate_f32", "rnn_oracle_locate_f64"):
+            getattr(_LIB, name).restype = ctypes.c_long
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def ctc(activations, flat_labels, label_lengths, input_lengths, blank=0,
+        want_grad=True, dtype=np.float32, num_threads=0):
+    """activations [T, B, A] float32 (time-major, as warp-ctc).  Returns
+    (costs[B], grads[T,B,A] or None) in `dtype` (float32 | float64)."""
+    act = np.ascontiguousarray(activations, dtype=np.float32)
+    T, B, A = act.shape
+    ll = np.ascontiguousarray(label_lengths, dtype=np.int32)
+    il = np.ascontiguousarray(input_lengths, dtype=np.int32)
+    fl = np.ascontiguousarray(flat_labels, dtype=np.int32)
+    assert T == int(il.max()), "slab length must equal max(input_lengths)"
+    costs = np.zeros(B, dtype=dtype)
+    grads = np.zeros((T, B, A), dtype=dtype) if want_grad else None
+    fn = lib().ctc_oracle_f32 if dtype == np.float32 else lib().ctc_oracle_f64
+    st = fn(_p(act), _p(grads), _p(fl), _p(ll), _p(il), ctypes.c_int(A),
+            ctypes.c_int(B), _p(costs), ctypes.c_int(blank),
+            ctypes.c_int(num_threads))
+    if st != 0:
+        raise ValueError("ctc oracle status %d" % st)
+    return costs, grads
+
+
+def rnn_param_count(mode, bidir, layers, D, H):
+    return int(lib().rnn_oracle_param_count_f32(mode, int(bidir), layers, D, H))
+
+
+def rnn_locate(mode, bidir, layers, D, H, p, lin, is_bias):
+    r, c = ctypes.c_int(), ctypes.c_int()
+    off = lib().rnn_oracle_locate_f32(mode, int(bidir), layers, D, H, p, lin,
+                                      int(is_bias), ctypes.byref(r),
+                                      ctypes.byref(c))
+    return int(off), r.value, c.value
+
+
+def rnn(mode, bidir, layers, H, x, w, B, dy=None, dtype=np.float32,
+        num_threads=0):
+    """x [T*B, D] float32 rows t*B+b; w packed blob float32.
+    Returns y [T*B, H*dirs]; with dy also (dx, dw)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    TB, D = x.shape
+    T = TB // B
+    dirs = 2 if bidir else 1
+    assert w.size == rnn_param_count(mode, bidir, layers, D, H)
+    y = np.zeros((TB, H * dirs), dtype=dtype)
+    fn = lib().rnn_oracle_f32 if dtype == np.float32 else lib().rnn_oracle_f64
+    if dy is None:
+        st = fn(mode, int(bidir), layers, D, H, B, T, _p(x), _p(w), _p(y), None,
+                None, None, num_threads)
+        assert st == 0
+        return y
+    dy = np.ascontiguousarray(dy, dtype=dtype)
+    dx = np.zeros((TB, D), dtype=dtype)
+    dw = np.zeros(w.size, dtype=dtype)
+    st = fn(mode, int(bidir), layers, D, H, B, T, _p(x), _p(w), _p(y), _p(dy),
+            _p(dx), _p(dw), num_threads)
+    assert st == 0
+    return y, dx, dw
