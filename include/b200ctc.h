@@ -1,0 +1,58 @@
+/*
+ * include/b200ctc.h -- extended entry points of libb200ctc.so for callers that
+ * want to drop the per-minibatch overheads around the warp-ctc call in
+ * NnetCtcUpdater::ComputeObjfAndDeriv (src/ctc/ctc-nnet-update.cc:171-259):
+ *   - cudaStreamCreate/Destroy + cudaMalloc/cudaFree per minibatch (:209-217,
+ *     247-248)  -> caller-owned workspace, any stream, optional no-sync
+ *   - deriv->Scale(-1) in NnetCtcUpdater::Backprop (:323) -> grad_scale
+ *   - deriv->Sum() NaN check (:232-234) -> *nonfinite flag written by the kernel
+ * Same data layout and semantics as include/ctc.h.
+ */
+#ifndef B200CTC_H_
+#define B200CTC_H_
+
+#include "ctc.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+  int blank_label;    /* 0 in kaldi-ctc */
+  float grad_scale;   /* gradients are multiplied by this (1 = warp-ctc, -1 =
+                         what NnetCtcUpdater::Backprop feeds the network) */
+  CUstream stream;    /* stream to enqueue on */
+  int no_sync;        /* 1: do not synchronise; costs_host may then be NULL and
+                         costs are only available in costs_dev */
+} b200ctcOptions;
+
+/* Same as get_workspace_size. */
+ctcStatus_t b200ctc_workspace_size(const int *label_lengths,
+                                   const int *input_lengths, int alphabet_size,
+                                   int minibatch, size_t *size_bytes);
+
+/*
+ * costs_host (HOST, may be NULL when no_sync) and costs_dev (DEVICE, may be
+ * NULL) both receive the per-utterance NLL.  Everything else as
+ * compute_ctc_loss.
+ */
+ctcStatus_t b200ctc_loss(const float *activations, float *gradients,
+                         const int *flat_labels, const int *label_lengths,
+                         const int *input_lengths, int alphabet_size,
+                         int minibatch, float *costs_host, float *costs_dev,
+                         void *workspace, size_t workspace_bytes,
+                         b200ctcOptions options);
+
+/* Algorithmic HBM bytes of one call:
+ * 4*A*sum_b T_b + 4*A*T_max*B + 4*sum L_b + 4*B. */
+size_t b200ctc_algorithmic_bytes(const int *label_lengths,
+                                 const int *input_lengths, int alphabet_size,
+                                 int minibatch);
+
+/* Number of kernels one b200ctc_loss call launches (for bench.py's count). */
+int b200ctc_launches_per_call(int with_gradients);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CTC_H_ */

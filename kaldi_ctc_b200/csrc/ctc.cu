@@ -1,0 +1,780 @@
+// kaldi_ctc_b200/csrc/ctc.cu
+//
+// CTC loss + gradient for sm_100a behind the warp-ctc C ABI (include/ctc.h).
+// Replaces the library call at src/ctc/ctc-nnet-update.cc:211-243 of the
+// reference (get_workspace_size + compute_ctc_loss).
+//
+// Three kernels per call, all on the caller's stream:
+//   K1 ctc_rowstats_gather   one warp per (t,b) row: online log-sum-exp of the
+//        row (one HBM read of the activations), and a gather of the emission
+//        log-probabilities of the utterance's own lattice symbols (blank + its
+//        L labels) into a compact per-utterance table E[t][u], base-2 logs.
+//   K2 ctc_alpha_beta<P>     one CTA per utterance.  Two warp groups run the
+//        alpha (forward) and beta (backward) recursions CONCURRENTLY over the
+//        blank-interleaved lattice, P (blank,label) state pairs per thread,
+//        neighbour states by warp shuffle (+ one smem word per warp boundary),
+//        emissions staged into shared memory by TMA bulk copies
+//        (cp.async.bulk + mbarrier, 4-stage ring per direction).  Log-space,
+//        base 2, renormalised every kRenorm frames with the running offset kept
+//        in double, so |alpha| stays small and fp32 keeps ~1e-6 resolution
+//        (un-normalised fp32 alphas lose 5e-4 at |log p| ~ 8000).
+//   K3 ctc_grad              one warp per row: y = softmax(row) (second HBM
+//        read), state posteriors gamma_t(s) from alpha, beta, E (normalised per
+//        frame so the common-mode rounding of the two recursions cancels),
+//        per-label sums through a label->states CSR built on the host, and ONE
+//        coalesced float4 write of the gradient row.  Padded rows are zeroed.
+//
+// HBM traffic: 2 reads + 1 write of the [T,B,A] slab, + the compact
+// per-utterance tables (E, alpha, beta: 5*(L+1)*4 B per frame).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "../../include/b200ctc.h"
+
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr double kLn2 = 0.6931471805599453;
+constexpr float kNeg = -1.0e30f;  // "log 0": absorbs every finite addend
+constexpr int kStages = 4;        // TMA ring depth per direction
+constexpr int kStageFloats = 2048;  // 8 KB per stage
+constexpr int kRenorm = 16;       // frames between renormalisations
+constexpr int kK1Warps = 8;
+constexpr int kK3Warps = 8;
+
+struct UttMeta {
+  int T;          // input length
+  int L;          // label length
+  int lab_off;    // offset into flat labels
+  int pitch;      // floats per frame of E (>= L+1, multiple of 4)
+  int feasible;   // L + repeats <= T
+  int csr_off;    // offset into uniq_lab / uniq_start (L+1 entries reserved +1)
+  int nuniq;      // number of distinct labels
+  int pad_;
+  long long e_off;   // float offset of E_b
+  long long ab_off;  // float offset of alpha_b / beta_b (2*pitch per frame)
+  long long fr_off;  // frame offset into offA/offB
+};
+
+struct CtcDev {
+  const float *act;
+  float *grad;
+  int A, B, Tmax, blank;
+  float grad_scale;
+  const UttMeta *meta;
+  const int *labels;      // flat labels
+  const int *uniq_lab;    // per utt: distinct labels (ascending)
+  const int *uniq_start;  // per utt: nuniq+1 offsets into pos
+  const int *pos;         // per utt: label positions grouped by label
+  float *lse2;            // [Tmax*B] base-2 log-sum-exp of each row
+  float *E;
+  float *alpha;
+  float *beta;            // shifted by one state: beta[s+1]
+  double *offA, *offB;    // per frame renormalisation offsets (base 2)
+  double *logp2;          // [2*B]: alpha-side and beta-side log2 p(l|x)
+  float *costs;           // [B]
+  int *flags;             // [0]: non-finite cost seen
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// log2(2^a + 2^b)
+__device__ __forceinline__ float lse2_2(float a, float b) {
+  float m = fmaxf(a, b), d = fminf(a, b) - m;
+  return m + lg2_approx(1.0f + ex2_approx(d));
+}
+// log2(2^a + 2^b + 2^c): the largest term is exactly 1 after the shift
+__device__ __forceinline__ float lse2_3(float a, float b, float c) {
+  float hi = fmaxf(a, b), lo = fminf(a, b);
+  float m = fmaxf(hi, c);
+  float mid = fmaxf(lo, fminf(hi, c));
+  float mn = fminf(lo, c);
+  return m + lg2_approx(1.0f + ex2_approx(mid - m) + ex2_approx(mn - m));
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- mbarrier / TMA bulk helpers (PTX) -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// 1-D TMA: global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes,
+                                            uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ===========================================================================
+// K1: per-row log-sum-exp + gather of the lattice emissions
+// ===========================================================================
+__global__ void __launch_bounds__(kK1Warps * 32)
+ctc_rowstats_gather_kernel(CtcDev d) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * kK1Warps + (threadIdx.x >> 5);
+  if (row >= (long long)d.Tmax * d.B) return;
+  const int t = (int)(row / d.B), b = (int)(row - (long long)t * d.B);
+  const UttMeta um = d.meta[b];
+  if (t >= um.T || !um.feasible) return;
+  const int A = d.A;
+  const float *a = d.act + row * A;
+
+  float m = -3.0e38f, s = 0.f;
+  if ((A & 3) == 0) {
+    const float4 *a4 = reinterpret_cast<const float4 *>(a);
+    const int n4 = A >> 2;
+    for (int k = lane; k < n4; k += 128) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        v[u] = (k + 32 * u < n4) ? __ldg(a4 + k + 32 * u)
+                                 : make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
+        if (mx > m) {
+          s *= exp2f((m - mx) * kLog2e);
+          m = mx;
+        }
+        s += exp2f((v[u].x - m) * kLog2e) + exp2f((v[u].y - m) * kLog2e) +
+             exp2f((v[u].z - m) * kLog2e) + exp2f((v[u].w - m) * kLog2e);
+      }
+    }
+  } else {
+    for (int k = lane; k < A; k += 32) {
+      float v = __ldg(a + k);
+      if (v > m) {
+        s *= exp2f((m - v) * kLog2e);
+        m = v;
+      }
+      s += exp2f((v - m) * kLog2e);
+    }
+  }
+  const float M = warp_max(m);
+  s *= exp2f((m - M) * kLog2e);
+  const float S = warp_sum(s);
+  const float l2 = M * kLog2e + log2f(S);
+  if (lane == 0) d.lse2[row] = l2;
+
+  // gather: E[t][0] = blank, E[t][1+i] = label i  (base-2 log-probabilities)
+  float *e = d.E + um.e_off + (long long)t * um.pitch;
+  const int *lab = d.labels + um.lab_off;
+  for (int u = lane; u <= um.L; u += 32) {
+    const int k = u == 0 ? d.blank : __ldg(lab + u - 1);
+    e[u] = __ldg(a + k) * kLog2e - l2;
+  }
+}
+
+// ===========================================================================
+// K2: concurrent alpha / beta recursions, one CTA per utterance
+// ===========================================================================
+// Pair i (0..L) = {Y_i: a blank state, X_i: the label state after it (alpha) /
+// before it (beta)}.  With the label string reversed, beta obeys the SAME
+// recurrence as alpha, so both warp groups run this code:
+//   Y_i <- Eb   + lse(Y_i, X_{i-1})
+//   X_i <- El_i + lse(X_i, Y_i, skip_i ? X_{i-1} : 0)
+// alpha: Y_i = state 2i, X_i = state 2i+1, time ascending, label i.
+// beta : Y_i = state 2(L-i), X_i = state 2(L-i)-1, time descending, label L-1-i.
+template <int P>
+__global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int frames_per_stage) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);               // [2][kStages]
+  float *bnd = reinterpret_cast<float *>(smem_raw + 64);                 // [2][2][32]
+  float *red = bnd + 128;                                                // [2][32]
+  float *fin = red + 64;                                                 // [2][2]
+  float *stages = reinterpret_cast<float *>(smem_raw + 1024);            // [2][kStages][kStageFloats]
+
+  const int b = blockIdx.x;
+  const UttMeta um = d.meta[b];
+  if (!um.feasible) return;
+  const int NT = blockDim.x >> 1;
+  const int role = threadIdx.x >= NT ? 1 : 0;
+  const int r = threadIdx.x - role * NT;
+  const int lane = r & 31, w = r >> 5;
+  const int L = um.L, T = um.T, pitch = um.pitch, F = frames_per_stage;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2 * kStages; i++) mbar_init(mbar + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int nthreads_needed = (L + 1 + P - 1) / P;
+  const int nwarps_active = (nthreads_needed + 31) >> 5;
+  if (w >= nwarps_active) return;  // idle warps leave; named barriers count the rest
+  const int nbar = nwarps_active * 32;
+
+  uint64_t *my_bar = mbar + role * kStages;
+  float *my_stage = stages + role * kStages * kStageFloats;
+  const float *Eg = d.E + um.e_off;
+  const int nchunks = (T + F - 1) / F;
+
+  // chunk k (in visiting order) -> first frame and frame count
+  auto chunk_lo = [&](int k) { return role ? max(0, T - (k + 1) * F) : k * F; };
+  auto chunk_n = [&](int k) { return min(F, T - k * F); };
+  auto issue = [&](int k) {
+    const int st = k % kStages;
+    const uint32_t bytes = (uint32_t)chunk_n(k) * pitch * 4u;
+    mbar_expect_tx(my_bar + st, bytes);
+    tma_load_1d(my_stage + st * kStageFloats, Eg + (long long)chunk_lo(k) * pitch, bytes,
+                my_bar + st);
+  };
+  if (r == 0)
+    for (int k = 0; k < min(kStages, nchunks); k++) issue(k);
+
+  // per-thread lattice slice
+  const int i0 = r * P;
+  const int *lab = d.labels + um.lab_off;
+  float X[P], Y[P];
+  int eidx[P];      // index of El_i inside a frame of E
+  bool skip[P], hasX[P], hasY[P];
+#pragma unroll
+  for (int p = 0; p < P; p++) {
+    const int i = i0 + p;
+    hasY[p] = i <= L;
+    hasX[p] = i < L;
+    int li = 0, lprev = -1;
+    if (hasX[p]) {
+      li = role ? lab[L - 1 - i] : lab[i];
+      if (i >= 1) lprev = role ? lab[L - i] : lab[i - 1];
+    }
+    skip[p] = hasX[p] && i >= 1 && li != lprev;
+    eidx[p] = hasX[p] ? (role ? L - i : 1 + i) : 0;
+    X[p] = kNeg;
+    Y[p] = (i == 0) ? 0.f : kNeg;  // virtual frame "-1": all mass on the first blank
+  }
+  float xin = kNeg;  // X_{i0-1} of the previous frame
+  double C = 0.0;    // renormalisation offset (thread r == 0 only)
+
+  float *out = (role ? d.beta : d.alpha) + um.ab_off;
+  double *off_out = (role ? d.offB : d.offA) + um.fr_off;
+  const int pitch2 = 2 * pitch;
+
+  for (int step = 0; step < T; step++) {
+    const int t = role ? T - 1 - step : step;
+    const int k = step / F;
+    const int st = k % kStages;
+    if (step - k * F == 0) mbar_wait(my_bar + st, (k / kStages) & 1);
+    const float *e = my_stage + st * kStageFloats + (t - chunk_lo(k)) * pitch;
+    const float Eb = e[0];
+    float El[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) El[p] = hasX[p] ? e[eidx[p]] : 0.f;
+
+    float nX[P], nY[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+      const float xp = p == 0 ? xin : X[p - 1];
+      nY[p] = Eb + lse2_2(Y[p], xp);
+      nX[p] = El[p] + lse2_3(X[p], Y[p], skip[p] ? xp : kNeg);
+    }
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+      Y[p] = hasY[p] ? nY[p] : kNeg;
+      X[p] = hasX[p] ? nX[p] : kNeg;
+    }
+    // store this frame (offset C applies to these values)
+    float *o = out + (long long)t * pitch2;
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+      const int i = i0 + p;
+      if (hasY[p]) {
+        if (role == 0)
+          *reinterpret_cast<float2 *>(o + 2 * i) = make_float2(Y[p], X[p]);
+        else
+          *reinterpret_cast<float2 *>(o + 2 * (L - i)) = make_float2(X[p], Y[p]);
+      }
+    }
+    if (r == 0) off_out[t] = C;
+
+    // hand X_{last} to the next thread for the next frame
+    const float xs = __shfl_up_sync(0xffffffffu, X[P - 1], 1);
+    float *bn = bnd + (role * 2 + (step & 1)) * 32;
+    if (lane == 31) bn[w] = X[P - 1];
+
+    const bool renorm = (step % kRenorm) == kRenorm - 1;
+    float wm = 0.f;
+    if (renorm) {
+      float mx = kNeg;
+#pragma unroll
+      for (int p = 0; p < P; p++) mx = fmaxf(mx, fmaxf(X[p], Y[p]));
+      wm = warp_max(mx);
+      if (lane == 0) red[role * 32 + w] = wm;
+    }
+    named_bar_sync(1 + role, nbar);
+    xin = lane == 0 ? (w == 0 ? kNeg : bn[w - 1]) : xs;
+
+    if (renorm) {
+      float Mx = kNeg;
+      for (int q = 0; q < nwarps_active; q++) Mx = fmaxf(Mx, red[role * 32 + q]);
+      if (Mx > -1.0e29f) {
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+          X[p] = fmaxf(X[p] - Mx, kNeg);
+          Y[p] = fmaxf(Y[p] - Mx, kNeg);
+        }
+        xin = fmaxf(xin - Mx, kNeg);
+        if (r == 0) C += (double)Mx;
+      }
+    }
+    // stage fully consumed -> refill it with the chunk kStages ahead
+    if (r == 0 && (step + 1 == (k + 1) * F) && k + kStages < nchunks) issue(k + kStages);
+  }
+
+  // log2 p(l|x) = C + lse(Y_L, X_{L-1})
+#pragma unroll
+  for (int p = 0; p < P; p++) {
+    const int i = i0 + p;
+    if (i == L) fin[role * 2 + 0] = Y[p];
+    if (i == L - 1) fin[role * 2 + 1] = X[p];
+  }
+  if (r == 0 && L == 0) fin[role * 2 + 1] = kNeg;
+  named_bar_sync(1 + role, nbar);
+  if (r == 0) {
+    const double lp2 = C + (double)lse2_2(fin[role * 2], fin[role * 2 + 1]);
+    d.logp2[role * d.B + b] = lp2;
+    if (role == 0) {
+      const float cost = (float)(-lp2 * kLn2);
+      d.costs[b] = cost;
+      if (!(fabsf(cost) < 3.0e38f)) atomicOr(d.flags, 1);
+    }
+  }
+}
+
+// ===========================================================================
+// K3: gradient rows
+// ===========================================================================
+__global__ void __launch_bounds__(kK3Warps * 32) ctc_grad_kernel(CtcDev d, int smem_pitch) {
+  extern __shared__ __align__(16) float gsm[];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const long long row = (long long)blockIdx.x * kK3Warps + wi;
+  if (row >= (long long)d.Tmax * d.B) return;
+  const int t = (int)(row / d.B), b = (int)(row - (long long)t * d.B);
+  const UttMeta um = d.meta[b];
+  const int A = d.A;
+  float *g = d.grad + row * A;
+  const bool vec = (A & 3) == 0;
+
+  if (t >= um.T || !um.feasible) {  // padded frame / unalignable utterance: zero row
+    if (vec) {
+      float4 *g4 = reinterpret_cast<float4 *>(g);
+      for (int k = lane; k < (A >> 2); k += 32) g4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int k = lane; k < A; k += 32) g[k] = 0.f;
+    }
+    return;
+  }
+  const float *a = d.act + row * A;
+  const float l2 = d.lse2[row];
+  const float gs = d.grad_scale;
+  const int L = um.L, S = 2 * L + 1, pitch = um.pitch;
+
+  // state posteriors gamma_t(s) ~ 2^(alpha + beta - E + offsets - log2 p)
+  const float *al = d.alpha + um.ab_off + (long long)t * 2 * pitch;
+  const float *be = d.beta + um.ab_off + (long long)t * 2 * pitch + 1;
+  const float *e = d.E + um.e_off + (long long)t * pitch;
+  const float D = (float)(d.offA[um.fr_off + t] + d.offB[um.fr_off + t] - d.logp2[b]);
+  float *sm = gsm + wi * smem_pitch;
+  float z = 0.f;
+  for (int s = lane; s < S; s += 32) {
+    const float ee = (s & 1) ? e[1 + (s >> 1)] : e[0];
+    const float v = exp2f(fmaxf(al[s] + be[s] - ee + D, -200.f));
+    sm[s] = v;
+    z += v;
+  }
+  const float Z = warp_sum(z);
+  const float zb = warp_sum((lane & 1) ? 0.f : z);  // even states are blanks
+  const float invZ = Z > 0.f ? 1.0f / Z : 0.f;
+
+  // y = softmax(row), streamed
+  if (vec) {
+    const float4 *a4 = reinterpret_cast<const float4 *>(a);
+    float4 *g4 = reinterpret_cast<float4 *>(g);
+    const int n4 = A >> 2;
+    for (int k = lane; k < n4; k += 128) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (k + 32 * u < n4) v[u] = __ldg(a4 + k + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (k + 32 * u < n4) {
+          float4 y;
+          y.x = gs * exp2f(v[u].x * kLog2e - l2);
+          y.y = gs * exp2f(v[u].y * kLog2e - l2);
+          y.z = gs * exp2f(v[u].z * kLog2e - l2);
+          y.w = gs * exp2f(v[u].w * kLog2e - l2);
+          g4[k + 32 * u] = y;
+        }
+    }
+  } else {
+    for (int k = lane; k < A; k += 32) g[k] = gs * exp2f(__ldg(a + k) * kLog2e - l2);
+  }
+  __syncwarp();  // orders the row stores above before the per-label overwrites below
+
+  if (lane == 0) g[d.blank] = gs * (exp2f(__ldg(a + d.blank) * kLog2e - l2) - zb * invZ);
+  const int *ul = d.uniq_lab + um.csr_off;
+  const int *us = d.uniq_start + um.csr_off + b;  // nuniq+1 entries per utterance
+  const int *pos = d.pos + um.lab_off;
+  for (int j = lane; j < um.nuniq; j += 32) {
+    const int kk = ul[j];
+    float acc = 0.f;
+    for (int q = us[j]; q < us[j + 1]; q++) acc += sm[2 * pos[q] + 1];
+    g[kk] = gs * (exp2f(__ldg(a + kk) * kLog2e - l2) - acc * invZ);
+  }
+}
+
+// ===========================================================================
+// host side
+// ===========================================================================
+struct Plan {
+  int A, B, Tmax, maxL, pitch_max;
+  long long sumT, sumL;
+  size_t off_meta, off_labels, off_uniq_lab, off_uniq_start, off_pos;  // header block
+  size_t header_bytes;
+  size_t off_lse2, off_E, off_alpha, off_beta, off_offA, off_offB, off_logp2, off_costs, off_flags;
+  size_t total;
+  std::vector<UttMeta> meta;
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int A, int B, Plan *p) {
+  if (!label_lengths || !input_lengths || A <= 0 || B <= 0) return CTC_STATUS_INVALID_VALUE;
+  p->A = A;
+  p->B = B;
+  p->Tmax = 0;
+  p->maxL = 0;
+  p->sumT = p->sumL = 0;
+  p->meta.assign(B, UttMeta());
+  long long e_off = 0, ab_off = 0;
+  for (int b = 0; b < B; b++) {
+    const int T = input_lengths[b], L = label_lengths[b];
+    if (T <= 0 || L < 0) return CTC_STATUS_INVALID_VALUE;
+    UttMeta &m = p->meta[b];
+    m.T = T;
+    m.L = L;
+    m.lab_off = (int)p->sumL;
+    m.pitch = (int)align_up((size_t)L + 1, 4);
+    m.csr_off = (int)p->sumL;
+    m.e_off = e_off;
+    m.ab_off = ab_off;
+    m.fr_off = p->sumT;
+    e_off += (long long)T * m.pitch;
+    ab_off += (long long)T * 2 * m.pitch;
+    p->sumT += T;
+    p->sumL += L;
+    p->Tmax = std::max(p->Tmax, T);
+    p->maxL = std::max(p->maxL, L);
+  }
+  p->pitch_max = (int)align_up((size_t)p->maxL + 1, 4);
+  if (p->maxL + 1 > 512 * 4) return CTC_STATUS_INVALID_VALUE;  // P <= 4, 512 threads per direction
+  size_t o = 0;
+  p->off_meta = o;        o = align_up(o + sizeof(UttMeta) * B, 256);
+  p->off_labels = o;      o = align_up(o + sizeof(int) * (p->sumL + 1), 256);
+  p->off_uniq_lab = o;    o = align_up(o + sizeof(int) * (p->sumL + 1), 256);
+  p->off_uniq_start = o;  o = align_up(o + sizeof(int) * (p->sumL + B + 1), 256);
+  p->off_pos = o;         o = align_up(o + sizeof(int) * (p->sumL + 1), 256);
+  p->header_bytes = o;
+  p->off_lse2 = o;   o = align_up(o + sizeof(float) * (size_t)p->Tmax * B, 256);
+  p->off_E = o;      o = align_up(o + sizeof(float) * (size_t)e_off, 256);
+  p->off_alpha = o;  o = align_up(o + sizeof(float) * (size_t)ab_off, 256);
+  p->off_beta = o;   o = align_up(o + sizeof(float) * (size_t)ab_off, 256);
+  p->off_offA = o;   o = align_up(o + sizeof(double) * (size_t)p->sumT, 256);
+  p->off_offB = o;   o = align_up(o + sizeof(double) * (size_t)p->sumT, 256);
+  p->off_logp2 = o;  o = align_up(o + sizeof(double) * 2 * B, 256);
+  p->off_costs = o;  o = align_up(o + sizeof(float) * B, 256);
+  p->off_flags = o;  o = align_up(o + 256, 256);
+  p->total = o;
+  return CTC_STATUS_SUCCESS;
+}
+
+// pinned staging for the header block (one H2D copy per call) and the costs
+struct Staging {
+  std::mutex mu;
+  unsigned char *pinned = nullptr;
+  size_t cap = 0;
+  float *costs = nullptr;
+  size_t costs_cap = 0;
+};
+Staging g_stage;
+
+bool ensure_pinned(Staging &s, size_t bytes, size_t ncosts) {
+  if (bytes > s.cap) {
+    if (s.pinned) cudaFreeHost(s.pinned);
+    s.pinned = nullptr;
+    s.cap = 0;
+    size_t want = align_up(bytes * 2, 4096);
+    if (cudaMallocHost(&s.pinned, want) != cudaSuccess) return false;
+    s.cap = want;
+  }
+  if (ncosts > s.costs_cap) {
+    if (s.costs) cudaFreeHost(s.costs);
+    s.costs = nullptr;
+    s.costs_cap = 0;
+    if (cudaMallocHost(&s.costs, sizeof(float) * ncosts * 2) != cudaSuccess) return false;
+    s.costs_cap = ncosts * 2;
+  }
+  return true;
+}
+
+template <int P>
+cudaError_t launch_k2(const CtcDev &dev, int B, int NT, int F, cudaStream_t stream) {
+  const size_t smem = 1024 + sizeof(float) * 2 * kStages * kStageFloats;
+  cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_kernel<P>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  ctc_alpha_beta_kernel<P><<<B, 2 * NT, smem, stream>>>(dev, F);
+  return cudaGetLastError();
+}
+
+ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int *label_lengths,
+                const int *input_lengths, int A, int B, float *costs_host, float *costs_dev,
+                void *workspace, size_t workspace_bytes, b200ctcOptions opt) {
+  if (!act || !flat_labels || !workspace || (!costs_host && !costs_dev))
+    return CTC_STATUS_INVALID_VALUE;
+  if (opt.blank_label < 0 || opt.blank_label >= A) return CTC_STATUS_INVALID_VALUE;
+  if ((uintptr_t)workspace % 256 != 0) return CTC_STATUS_INVALID_VALUE;
+  Plan p;
+  ctcStatus_t st = make_plan(label_lengths, input_lengths, A, B, &p);
+  if (st != CTC_STATUS_SUCCESS) return st;
+  if (workspace_bytes < p.total) return CTC_STATUS_INVALID_VALUE;
+  cudaStream_t stream = (cudaStream_t)opt.stream;
+
+  std::lock_guard<std::mutex> lock(g_stage.mu);
+  if (!ensure_pinned(g_stage, p.header_bytes, (size_t)B)) return CTC_STATUS_MEMOPS_FAILED;
+  unsigned char *h = g_stage.pinned;
+  memset(h, 0, p.header_bytes);
+  UttMeta *hm = reinterpret_cast<UttMeta *>(h + p.off_meta);
+  int *hl = reinterpret_cast<int *>(h + p.off_labels);
+  int *hul = reinterpret_cast<int *>(h + p.off_uniq_lab);
+  int *hus = reinterpret_cast<int *>(h + p.off_uniq_start);
+  int *hpos = reinterpret_cast<int *>(h + p.off_pos);
+  std::vector<int> order;
+  for (int b = 0; b < B; b++) {
+    UttMeta &m = p.meta[b];
+    const int *lab = flat_labels + m.lab_off;
+    int repeats = 0;
+    for (int i = 0; i < m.L; i++) {
+      if (lab[i] < 0 || lab[i] >= A || lab[i] == opt.blank_label) return CTC_STATUS_INVALID_VALUE;
+      if (i > 0 && lab[i] == lab[i - 1]) repeats++;
+      hl[m.lab_off + i] = lab[i];
+    }
+    m.feasible = (m.L + repeats <= m.T) ? 1 : 0;
+    // label -> positions CSR (positions ascending inside a label: fixed summation order)
+    order.resize(m.L);
+    for (int i = 0; i < m.L; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return lab[x] < lab[y]; });
+    int nu = 0;
+    int *us = hus + m.csr_off + b;
+    for (int q = 0; q < m.L; q++) {
+      hpos[m.lab_off + q] = order[q];
+      if (q == 0 || lab[order[q]] != lab[order[q - 1]]) {
+        hul[m.csr_off + nu] = lab[order[q]];
+        us[nu] = q;
+        nu++;
+      }
+    }
+    us[nu] = m.L;
+    m.nuniq = nu;
+    hm[b] = m;
+  }
+  unsigned char *w = static_cast<unsigned char *>(workspace);
+  if (cudaMemcpyAsync(w, h, p.header_bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess)
+    return CTC_STATUS_MEMOPS_FAILED;
+  if (cudaMemsetAsync(w + p.off_costs, 0, (p.off_flags + 256) - p.off_costs, stream) != cudaSuccess)
+    return CTC_STATUS_MEMOPS_FAILED;
+
+  CtcDev dev;
+  dev.act = act;
+  dev.grad = grad;
+  dev.A = A;
+  dev.B = B;
+  dev.Tmax = p.Tmax;
+  dev.blank = opt.blank_label;
+  dev.grad_scale = opt.grad_scale;
+  dev.meta = reinterpret_cast<const UttMeta *>(w + p.off_meta);
+  dev.labels = reinterpret_cast<const int *>(w + p.off_labels);
+  dev.uniq_lab = reinterpret_cast<const int *>(w + p.off_uniq_lab);
+  dev.uniq_start = reinterpret_cast<const int *>(w + p.off_uniq_start);
+  dev.pos = reinterpret_cast<const int *>(w + p.off_pos);
+  dev.lse2 = reinterpret_cast<float *>(w + p.off_lse2);
+  dev.E = reinterpret_cast<float *>(w + p.off_E);
+  dev.alpha = reinterpret_cast<float *>(w + p.off_alpha);
+  dev.beta = reinterpret_cast<float *>(w + p.off_beta);
+  dev.offA = reinterpret_cast<double *>(w + p.off_offA);
+  dev.offB = reinterpret_cast<double *>(w + p.off_offB);
+  dev.logp2 = reinterpret_cast<double *>(w + p.off_logp2);
+  dev.costs = reinterpret_cast<float *>(w + p.off_costs);
+  dev.flags = reinterpret_cast<int *>(w + p.off_flags);
+
+  const long long rows = (long long)p.Tmax * B;
+  const unsigned g1 = (unsigned)((rows + kK1Warps - 1) / kK1Warps);
+  ctc_rowstats_gather_kernel<<<g1, kK1Warps * 32, 0, stream>>>(dev);
+  if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
+
+  // K2 geometry: P pairs per thread so that one direction fits 512 threads
+  const int npairs = p.maxL + 1;
+  const int P = npairs <= 512 ? 1 : (npairs <= 1024 ? 2 : 4);
+  const int NT = (int)align_up((size_t)(npairs + P - 1) / P, 32);
+  const int F = std::max(1, std::min(32, kStageFloats / p.pitch_max));
+  cudaError_t ce = P == 1   ? launch_k2<1>(dev, B, NT, F, stream)
+                   : P == 2 ? launch_k2<2>(dev, B, NT, F, stream)
+                            : launch_k2<4>(dev, B, NT, F, stream);
+  if (ce != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
+
+  if (grad) {
+    const int smem_pitch = 2 * p.pitch_max;
+    const size_t smem3 = sizeof(float) * (size_t)kK3Warps * smem_pitch;
+    if (cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem3) != cudaSuccess)
+      return CTC_STATUS_EXECUTION_FAILED;
+    const unsigned g3 = (unsigned)((rows + kK3Warps - 1) / kK3Warps);
+    ctc_grad_kernel<<<g3, kK3Warps * 32, smem3, stream>>>(dev, smem_pitch);
+    if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
+  }
+  if (costs_dev &&
+      cudaMemcpyAsync(costs_dev, dev.costs, sizeof(float) * B, cudaMemcpyDeviceToDevice, stream) !=
+          cudaSuccess)
+    return CTC_STATUS_MEMOPS_FAILED;
+  if (!opt.no_sync) {
+    if (cudaMemcpyAsync(g_stage.costs, dev.costs, sizeof(float) * B, cudaMemcpyDeviceToHost,
+                        stream) != cudaSuccess)
+      return CTC_STATUS_MEMOPS_FAILED;
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+      fprintf(stderr, "b200ctc: %s\n", cudaGetErrorString(e));
+      return CTC_STATUS_EXECUTION_FAILED;
+    }
+    if (costs_host) memcpy(costs_host, g_stage.costs, sizeof(float) * B);
+  }
+  return CTC_STATUS_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+int get_warpctc_version(void) { return 2; }
+
+const char *ctcGetStatusString(ctcStatus_t status) {
+  switch (status) {
+    case CTC_STATUS_SUCCESS: return "no error";
+    case CTC_STATUS_MEMOPS_FAILED: return "cuda memcpy or memset failed";
+    case CTC_STATUS_INVALID_VALUE: return "invalid value";
+    case CTC_STATUS_EXECUTION_FAILED: return "execution failed";
+    default: return "unknown error";
+  }
+}
+
+ctcStatus_t b200ctc_workspace_size(const int *label_lengths, const int *input_lengths,
+                                   int alphabet_size, int minibatch, size_t *size_bytes) {
+  if (!size_bytes) return CTC_STATUS_INVALID_VALUE;
+  Plan p;
+  ctcStatus_t st = make_plan(label_lengths, input_lengths, alphabet_size, minibatch, &p);
+  if (st != CTC_STATUS_SUCCESS) return st;
+  *size_bytes = p.total;
+  return CTC_STATUS_SUCCESS;
+}
+
+ctcStatus_t get_workspace_size(const int *const label_lengths, const int *const input_lengths,
+                               int alphabet_size, int minibatch, struct ctcOptions options,
+                               size_t *size_bytes) {
+  if (options.loc != CTC_GPU) return CTC_STATUS_INVALID_VALUE;  // no CPU path in this library
+  return b200ctc_workspace_size(label_lengths, input_lengths, alphabet_size, minibatch, size_bytes);
+}
+
+ctcStatus_t b200ctc_loss(const float *activations, float *gradients, const int *flat_labels,
+                         const int *label_lengths, const int *input_lengths, int alphabet_size,
+                         int minibatch, float *costs_host, float *costs_dev, void *workspace,
+                         size_t workspace_bytes, b200ctcOptions options) {
+  try {
+    return run(activations, gradients, flat_labels, label_lengths, input_lengths, alphabet_size,
+               minibatch, costs_host, costs_dev, workspace, workspace_bytes, options);
+  } catch (...) {
+    return CTC_STATUS_UNKNOWN_ERROR;  // never throw across the C boundary
+  }
+}
+
+ctcStatus_t compute_ctc_loss(const float *const activations, float *gradients,
+                             const int *const flat_labels, const int *const label_lengths,
+                             const int *const input_lengths, int alphabet_size, int minibatch,
+                             float *costs, void *workspace, struct ctcOptions options) {
+  if (options.loc != CTC_GPU || !costs) return CTC_STATUS_INVALID_VALUE;
+  b200ctcOptions o;
+  o.blank_label = options.blank_label;
+  o.grad_scale = 1.0f;
+  o.stream = options.stream;
+  o.no_sync = 0;
+  size_t need = 0;
+  ctcStatus_t st = b200ctc_workspace_size(label_lengths, input_lengths, alphabet_size, minibatch, &need);
+  if (st != CTC_STATUS_SUCCESS) return st;
+  // the warp-ctc ABI carries no workspace size: the caller allocated get_workspace_size() bytes
+  return b200ctc_loss(activations, gradients, flat_labels, label_lengths, input_lengths,
+                      alphabet_size, minibatch, costs, nullptr, workspace, need, o);
+}
+
+size_t b200ctc_algorithmic_bytes(const int *label_lengths, const int *input_lengths,
+                                 int alphabet_size, int minibatch) {
+  size_t sumT = 0, sumL = 0;
+  int Tmax = 0;
+  for (int b = 0; b < minibatch; b++) {
+    sumT += input_lengths[b];
+    sumL += label_lengths[b];
+    Tmax = std::max(Tmax, input_lengths[b]);
+  }
+  return 4 * (size_t)alphabet_size * sumT + 4 * (size_t)alphabet_size * Tmax * minibatch +
+         4 * sumL + 4 * (size_t)minibatch;
+}
+
+int b200ctc_launches_per_call(int with_gradients) { return with_gradients ? 3 : 2; }
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+"""CPU-side checks of the drop-in boundary: the built libraries load and export
+every symbol include/*.h declares; host-only entry points (sizes, status strings,
+argument validation) behave like the reference expects."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+HEADERS = {
+    "libb200ctc.so": ["include/ctc.h", "include/b200ctc.h"],
+    "libb200rnn.so": ["include/b200rnn.h"],
+}
+
+
+def _declared_functions(header):
+    src = open(os.path.join(ROOT, header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//.*", "", src)
+    names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}]*\)\s*;", src)
+    return [n for n in names if n not in ("defined",)]
+
+
+@pytest.mark.parametrize("libname", sorted(HEADERS))
+def test_library_exports_every_declared_symbol(libname):
+    path = os.path.join(ROOT, "kaldi_ctc_b200", libname)
+    if not all(os.path.exists(os.path.join(ROOT, h)) for h in HEADERS[libname]):
+        pytest.skip("header not written yet")
+    if not os.path.exists(path):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(path)
+    for header in HEADERS[libname]:
+        if not os.path.exists(os.path.join(ROOT, header)):
+            pytest.skip(header + " not written yet")
+        names = _declared_functions(header)
+        assert names, header
+        for n in names:
+            assert hasattr(lib, n), "%s does not export %s (declared in %s)" % (libname, n, header)
+
+
+def test_ctc_host_only_entry_points():
+    from kaldi_ctc_b200 import ctc
+    L = ctc.lib()
+    assert L.ctcGetStatusString(0) == b"no error"
+    assert L.ctcGetStatusString(2) == b"invalid value"
+    n1 = ctc.workspace_size([150] * 16, [2000] * 16, 48)
+    n2 = ctc.workspace_size([150] * 32, [2000] * 32, 48)
+    assert 0 < n1 < n2
+    # 8*A*T*B (+ labels) for full-length utterances
+    assert ctc.algorithmic_bytes([150] * 16, [2000] * 16, 48) == 8 * 48 * 2000 * 16 + 4 * 150 * 16 + 4 * 16
+    with pytest.raises(ctc.CtcError):
+        ctc.workspace_size([3], [0], 5)          # empty utterance
+    with pytest.raises(ctc.CtcError):
+        ctc.workspace_size([5000], [20000], 5)   # beyond the supported label length
+    # CTC_CPU is not provided by this library: no CPU fallback behind the ABI
+    opt = ctc.CtcOptions()
+    opt.loc = 0
+    n = ctypes.c_size_t()
+    ll = np.array([1], np.int32)
+    assert L.get_workspace_size(ll.ctypes.data, ll.ctypes.data, 4, 1, opt, ctypes.byref(n)) == 2
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "kaldi_ctc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in txt and "liboracle" not in txt and "oracle/" not in txt, f

@@ -1,0 +1,151 @@
+"""Parity of the CUDA CTC path (libb200ctc.so, through the warp-ctc C ABI) with
+the oracle.  Tolerances are north_star's: loss 1e-5 relative, gradient 1e-4
+max-abs -- held against the fp64 instantiation of the oracle (and the committed
+torch-fp64 goldens), which is stricter than matching the fp32 one."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_ATOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    from kaldi_ctc_b200 import ctc
+    assert torch.cuda.is_available()
+    return torch, ctc, ctc.CtcLoss("cuda:0")
+
+
+def _run(ctx, act, fl, ll, il, **kw):
+    torch, ctc, op = ctx
+    a = torch.from_numpy(np.ascontiguousarray(act)).cuda()
+    costs, grad = op.compute(a, fl, ll, il, **kw)
+    torch.cuda.synchronize()
+    return costs, (grad.cpu().numpy() if grad is not None else None)
+
+
+def _check(costs, grad, c_ref, g_ref):
+    np.testing.assert_allclose(costs, c_ref, rtol=LOSS_RTOL)
+    assert np.abs(grad - g_ref).max() < GRAD_ATOL
+
+
+@pytest.mark.parametrize("name", ["ctc_small", "ctc_repeats", "ctc_ragged", "ctc_peaky", "ctc_wide"])
+def test_matches_committed_golden(ctx, golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    costs, grad = _run(ctx, z["activations"], z["flat_labels"], z["label_lengths"], z["input_lengths"])
+    _check(costs, grad, z["costs"], z["grads"])
+
+
+@pytest.mark.parametrize("cfg,peaky", [(1, False), (1, True), (4, False)])
+def test_baseline_configs_against_fp64_oracle(ctx, cfg, peaky):
+    from kaldi_ctc_b200 import synth
+    from oracle import pyoracle
+    bt = synth.config_ctc(cfg, peaky=peaky)
+    c_ref, g_ref = pyoracle.ctc(bt.activations, bt.flat_labels, bt.label_lengths, bt.input_lengths,
+                                dtype=np.float64)
+    costs, grad = _run(ctx, bt.activations, bt.flat_labels, bt.label_lengths, bt.input_lengths)
+    _check(costs, grad, c_ref, g_ref)
+    for b, Tb in enumerate(bt.input_lengths):
+        assert np.all(grad[Tb:, b, :] == 0)   # padded rows exactly zero
+    # the fp32 restatement of warp-ctc's arithmetic agrees to ITS accuracy
+    c32, g32 = pyoracle.ctc(bt.activations, bt.flat_labels, bt.label_lengths, bt.input_lengths,
+                            dtype=np.float32)
+    np.testing.assert_allclose(costs, c32, rtol=LOSS_RTOL)
+    assert np.abs(grad - g32).max() < np.abs(g32 - g_ref).max() + GRAD_ATOL
+
+
+def test_wide_alphabet_slice_of_config5(ctx):
+    """Config 5 (A=4000) at B=4: parity with the oracle + row-sum property."""
+    from kaldi_ctc_b200 import synth
+    from oracle import pyoracle
+    bt = synth.ctc_batch(4, 4000, 300, 500, 50, 200, seed=1005, sigma=2.0)
+    c_ref, g_ref = pyoracle.ctc(bt.activations, bt.flat_labels, bt.label_lengths, bt.input_lengths,
+                                dtype=np.float64)
+    costs, grad = _run(ctx, bt.activations, bt.flat_labels, bt.label_lengths, bt.input_lengths)
+    _check(costs, grad, c_ref, g_ref)
+    assert np.abs(grad.sum(-1)).max() < 1e-4
+
+
+@pytest.mark.parametrize("L,T,A", [(0, 7, 5), (1, 3, 4), (511, 1100, 40), (512, 1100, 40),
+                                   (700, 1500, 31), (1500, 3100, 9), (2047, 4100, 6)])
+def test_label_length_edges(ctx, L, T, A):
+    """L=0 (blank only), and every pairs-per-thread variant (P=1: L<=511, P=2: L<=1023,
+    P=4: L<=2047).  The reference's warp-ctc stopped at L=639 (ctc-nnet-train.cc:25-26)."""
+    from oracle import pyoracle
+    rng = np.random.default_rng(L + T)
+    act = (rng.standard_normal((T, 2, A)) * 2).astype(np.float32)
+    labs = [rng.integers(1, A, size=L).astype(np.int32), rng.integers(1, A, size=max(L - 1, 0)).astype(np.int32)]
+    il = np.array([T, T - 1], np.int32)
+    act[T - 1:, 1, :] = 0
+    fl = np.concatenate(labs) if L else np.zeros(0, np.int32)
+    ll = np.array([len(l) for l in labs], np.int32)
+    c_ref, g_ref = pyoracle.ctc(act, fl, ll, il, dtype=np.float64)
+    costs, grad = _run(ctx, act, fl, ll, il)
+    _check(costs, grad, c_ref, g_ref)
+
+
+def test_alphabet_not_multiple_of_four_and_nonzero_blank(ctx):
+    from oracle import pyoracle
+    rng = np.random.default_rng(2)
+    T, B, A, blank = 50, 3, 7, 3
+    act = rng.standard_normal((T, B, A)).astype(np.float32)
+    labs = [np.array([1, 1, 2, 6], np.int32), np.array([5], np.int32), np.array([0, 4, 0], np.int32)]
+    fl, ll, il = np.concatenate(labs), np.array([4, 1, 3], np.int32), np.array([50, 20, 33], np.int32)
+    for b in range(B):
+        act[il[b]:, b, :] = 0
+    c_ref, g_ref = pyoracle.ctc(act, fl, ll, il, blank=blank, dtype=np.float64)
+    costs, grad = _run(ctx, act, fl, ll, il, blank=blank)
+    _check(costs, grad, c_ref, g_ref)
+
+
+def test_loss_only_and_infeasible_and_errors(ctx):
+    torch, ctc, op = ctx
+    from oracle import pyoracle
+    rng = np.random.default_rng(3)
+    act = rng.standard_normal((6, 2, 5)).astype(np.float32)
+    fl, ll, il = np.array([1, 1, 1, 2], np.int32), np.array([3, 1], np.int32), np.array([4, 6], np.int32)
+    act[4:, 0, :] = 0
+    # utterance 0: L + repeats = 5 > T = 4 -> cost 0, zero gradient (warp-ctc behaviour)
+    costs, grad = _run(ctx, act, fl, ll, il)
+    c_ref, g_ref = pyoracle.ctc(act, fl, ll, il, dtype=np.float64)
+    assert costs[0] == 0 and np.all(grad[:, 0, :] == 0)
+    _check(costs, grad, c_ref, g_ref)
+    costs2, none = _run(ctx, act, fl, ll, il, want_grad=False)
+    assert none is None
+    np.testing.assert_array_equal(costs, costs2)
+    a = torch.from_numpy(act).cuda()
+    with pytest.raises(ctc.CtcError):
+        op.compute(a, np.array([0, 1, 1, 2], np.int32), ll, il)   # blank inside the labels
+    with pytest.raises(ctc.CtcError):
+        op.compute(a, np.array([5, 1, 1, 2], np.int32), ll, il)   # label >= alphabet
+
+
+def test_extended_entry_point(ctx):
+    """b200ctc_loss: grad_scale=-1 (fuses NnetCtcUpdater::Backprop's Scale(-1),
+    ctc-nnet-update.cc:323), device costs, no host sync."""
+    torch, ctc, op = ctx
+    from kaldi_ctc_b200 import synth
+    bt = synth.ctc_batch(5, 33, 60, 90, 5, 20, seed=9)
+    a = torch.from_numpy(bt.activations).cuda()
+    costs, grad = op.compute(a, bt.flat_labels, bt.label_lengths, bt.input_lengths)
+    g2 = torch.full_like(a, 7.0)
+    cd = torch.zeros(5, device="cuda")
+    op.compute_extended(a, bt.flat_labels, bt.label_lengths, bt.input_lengths, gradients=g2,
+                        grad_scale=-1.0, costs_dev=cd, no_sync=True)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(cd.cpu().numpy(), costs)
+    np.testing.assert_array_equal(g2.cpu().numpy(), -grad.cpu().numpy())
+
+
+def test_deterministic(ctx):
+    from kaldi_ctc_b200 import synth
+    bt = synth.ctc_batch(8, 48, 300, 400, 60, 90, seed=4)
+    r1 = _run(ctx, bt.activations, bt.flat_labels, bt.label_lengths, bt.input_lengths)
+    r2 = _run(ctx, bt.activations, bt.flat_labels, bt.label_lengths, bt.input_lengths)
+    np.testing.assert_array_equal(r1[0], r2[0])
+    np.testing.assert_array_equal(r1[1], r2[1])
