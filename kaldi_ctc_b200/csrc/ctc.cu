@@ -15,9 +15,11 @@
 //        neighbour states by warp shuffle (+ one smem word per warp boundary),
 //        emissions staged into shared memory by TMA bulk copies
 //        (cp.async.bulk + mbarrier, 4-stage ring per direction).  Log-space,
-//        base 2, renormalised every kRenorm frames with the running offset kept
-//        in double, so |alpha| stays small and fp32 keeps ~1e-6 resolution
-//        (un-normalised fp32 alphas lose 5e-4 at |log p| ~ 8000).
+//        base 2.  Every thread keeps its states relative to its OWN integer
+//        offset, re-centred every kRenorm frames without any block-wide
+//        reduction, so the stored values stay within ~+-100 and fp32 keeps
+//        ~1e-5 resolution exactly where the posteriors live (un-normalised
+//        fp32 alphas, as in warp-ctc, lose 5e-4 at |log p| ~ 8000).
 //   K3 ctc_grad              one warp per row: y = softmax(row) (second HBM
 //        read), state posteriors gamma_t(s) from alpha, beta, E (normalised per
 //        frame so the common-mode rounding of the two recursions cancels),
@@ -44,7 +46,7 @@ constexpr double kLn2 = 0.6931471805599453;
 constexpr float kNeg = -1.0e30f;  // "log 0": absorbs every finite addend
 constexpr int kStages = 4;        // TMA ring depth per direction
 constexpr int kStageFloats = 2048;  // 8 KB per stage
-constexpr int kRenorm = 16;       // frames between renormalisations
+constexpr int kRenorm = 8;        // frames between per-thread re-centrings
 constexpr int kK1Warps = 8;
 constexpr int kK3Warps = 8;
 
@@ -59,7 +61,7 @@ struct UttMeta {
   int pad_;
   long long e_off;   // float offset of E_b
   long long ab_off;  // float offset of alpha_b / beta_b (2*pitch per frame)
-  long long fr_off;  // frame offset into offA/offB
+  long long off_off; // float offset of this utterance's offset tables
 };
 
 struct CtcDev {
@@ -76,7 +78,8 @@ struct CtcDev {
   float *E;
   float *alpha;
   float *beta;            // shifted by one state: beta[s+1]
-  double *offA, *offB;    // per frame renormalisation offsets (base 2)
+  float *offA, *offB;     // [utt][frame block][thread] integer offsets of alpha / beta
+  int P;                  // state pairs per thread in K2
   double *logp2;          // [2*B]: alpha-side and beta-side log2 p(l|x)
   float *costs;           // [B]
   int *flags;             // [0]: non-finite cost seen
@@ -227,10 +230,9 @@ template <int P>
 __global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int frames_per_stage) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);               // [2][kStages]
-  float *bnd = reinterpret_cast<float *>(smem_raw + 64);                 // [2][2][32]
-  float *red = bnd + 128;                                                // [2][32]
-  float *fin = red + 64;                                                 // [2][2]
-  float *stages = reinterpret_cast<float *>(smem_raw + 1024);            // [2][kStages][kStageFloats]
+  float2 *bnd = reinterpret_cast<float2 *>(smem_raw + 64);               // [2][2][32] (value, offset)
+  float *fin = reinterpret_cast<float *>(smem_raw + 64 + 1024);          // [2][4]
+  float *stages = reinterpret_cast<float *>(smem_raw + 2048);            // [2][kStages][kStageFloats]
 
   const int b = blockIdx.x;
   const UttMeta um = d.meta[b];
@@ -291,11 +293,15 @@ __global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int f
     X[p] = kNeg;
     Y[p] = (i == 0) ? 0.f : kNeg;  // virtual frame "-1": all mass on the first blank
   }
-  float xin = kNeg;  // X_{i0-1} of the previous frame
-  double C = 0.0;    // renormalisation offset (thread r == 0 only)
+  // Values are kept relative to a per-thread integer offset c (a float holding an
+  // integer): true log2 value = stored + c.  A thread whose states are all still
+  // unreachable simply adopts its neighbour's offset.
+  float xin = kNeg;  // X_{i0-1} of the previous frame, already relative to c
+  float c = 0.f;
+  bool live = (r == 0);
 
   float *out = (role ? d.beta : d.alpha) + um.ab_off;
-  double *off_out = (role ? d.offB : d.offA) + um.fr_off;
+  float *off_out = (role ? d.offB : d.offA) + um.off_off;
   const int pitch2 = 2 * pitch;
 
   for (int step = 0; step < T; step++) {
@@ -316,12 +322,15 @@ __global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int f
       nY[p] = Eb + lse2_2(Y[p], xp);
       nX[p] = El[p] + lse2_3(X[p], Y[p], skip[p] ? xp : kNeg);
     }
+    float mx = kNeg;
 #pragma unroll
     for (int p = 0; p < P; p++) {
-      Y[p] = hasY[p] ? nY[p] : kNeg;
-      X[p] = hasX[p] ? nX[p] : kNeg;
+      Y[p] = hasY[p] ? fmaxf(nY[p], kNeg) : kNeg;
+      X[p] = hasX[p] ? fmaxf(nX[p], kNeg) : kNeg;
+      mx = fmaxf(mx, fmaxf(X[p], Y[p]));
     }
-    // store this frame (offset C applies to these values)
+    live = live || (mx > -1.0e29f);
+    // store this frame (relative to c)
     float *o = out + (long long)t * pitch2;
 #pragma unroll
     for (int p = 0; p < P; p++) {
@@ -333,53 +342,60 @@ __global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int f
           *reinterpret_cast<float2 *>(o + 2 * (L - i)) = make_float2(X[p], Y[p]);
       }
     }
-    if (r == 0) off_out[t] = C;
-
-    // hand X_{last} to the next thread for the next frame
-    const float xs = __shfl_up_sync(0xffffffffu, X[P - 1], 1);
-    float *bn = bnd + (role * 2 + (step & 1)) * 32;
-    if (lane == 31) bn[w] = X[P - 1];
-
-    const bool renorm = (step % kRenorm) == kRenorm - 1;
-    float wm = 0.f;
-    if (renorm) {
-      float mx = kNeg;
-#pragma unroll
-      for (int p = 0; p < P; p++) mx = fmaxf(mx, fmaxf(X[p], Y[p]));
-      wm = warp_max(mx);
-      if (lane == 0) red[role * 32 + w] = wm;
-    }
-    named_bar_sync(1 + role, nbar);
-    xin = lane == 0 ? (w == 0 ? kNeg : bn[w - 1]) : xs;
-
-    if (renorm) {
-      float Mx = kNeg;
-      for (int q = 0; q < nwarps_active; q++) Mx = fmaxf(Mx, red[role * 32 + q]);
-      if (Mx > -1.0e29f) {
+    // end of a frame block: publish the offset the block was stored with, re-centre
+    if ((step % kRenorm) == kRenorm - 1 || step == T - 1) {
+      off_out[(step / kRenorm) * nthreads_needed + r] = c;
+      if (mx > -1.0e29f) {
+        const float sh = floorf(mx);
 #pragma unroll
         for (int p = 0; p < P; p++) {
-          X[p] = fmaxf(X[p] - Mx, kNeg);
-          Y[p] = fmaxf(Y[p] - Mx, kNeg);
+          X[p] = fmaxf(X[p] - sh, kNeg);
+          Y[p] = fmaxf(Y[p] - sh, kNeg);
         }
-        xin = fmaxf(xin - Mx, kNeg);
-        if (r == 0) C += (double)Mx;
+        c += sh;
       }
     }
+    // hand (X_last, c) to the next thread for the next frame
+    const float xs = __shfl_up_sync(0xffffffffu, X[P - 1], 1);
+    const float cs = __shfl_up_sync(0xffffffffu, c, 1);
+    float2 *bn = bnd + (role * 2 + (step & 1)) * 32;
+    if (lane == 31) bn[w] = make_float2(X[P - 1], c);
+    named_bar_sync(1 + role, nbar);
+    float xv = xs, cv = cs;
+    if (lane == 0) {
+      const float2 v = w == 0 ? make_float2(kNeg, c) : bn[w - 1];
+      xv = v.x;
+      cv = v.y;
+    }
+    if (!live) c = cv;                 // nothing reachable here yet: follow the neighbour
+    xin = fmaxf(xv + (cv - c), kNeg);  // cv - c is an exact integer
     // stage fully consumed -> refill it with the chunk kStages ahead
     if (r == 0 && (step + 1 == (k + 1) * F) && k + kStages < nchunks) issue(k + kStages);
   }
 
-  // log2 p(l|x) = C + lse(Y_L, X_{L-1})
+  // log2 p(l|x) = lse(Y_L, X_{L-1}) in absolute terms
 #pragma unroll
   for (int p = 0; p < P; p++) {
     const int i = i0 + p;
-    if (i == L) fin[role * 2 + 0] = Y[p];
-    if (i == L - 1) fin[role * 2 + 1] = X[p];
+    if (i == L) {
+      fin[role * 4 + 0] = Y[p];
+      fin[role * 4 + 1] = c;
+    }
+    if (i == L - 1) {
+      fin[role * 4 + 2] = X[p];
+      fin[role * 4 + 3] = c;
+    }
   }
-  if (r == 0 && L == 0) fin[role * 2 + 1] = kNeg;
+  if (r == 0 && L == 0) {
+    fin[role * 4 + 2] = kNeg;
+    fin[role * 4 + 3] = 0.f;
+  }
   named_bar_sync(1 + role, nbar);
   if (r == 0) {
-    const double lp2 = C + (double)lse2_2(fin[role * 2], fin[role * 2 + 1]);
+    const double v0 = (double)fin[role * 4 + 0] + (double)fin[role * 4 + 1];
+    const double v1 = (double)fin[role * 4 + 2] + (double)fin[role * 4 + 3];
+    const double hi = fmax(v0, v1), lo = fmin(v0, v1);
+    const double lp2 = hi + log2(1.0 + exp2(fmax(lo - hi, -1000.0)));
     d.logp2[role * d.B + b] = lp2;
     if (role == 0) {
       const float cost = (float)(-lp2 * kLn2);
@@ -421,12 +437,18 @@ __global__ void __launch_bounds__(kK3Warps * 32) ctc_grad_kernel(CtcDev d, int s
   const float *al = d.alpha + um.ab_off + (long long)t * 2 * pitch;
   const float *be = d.beta + um.ab_off + (long long)t * 2 * pitch + 1;
   const float *e = d.E + um.e_off + (long long)t * pitch;
-  const float D = (float)(d.offA[um.fr_off + t] + d.offB[um.fr_off + t] - d.logp2[b]);
+  // offsets: alpha pair i = s/2 lives in thread i/P; beta pair i' = L - ceil(s/2)
+  const int P = d.P, nthr = (L + P) / P;
+  const float *oa = d.offA + um.off_off + (long long)(t / kRenorm) * nthr;
+  const float *ob = d.offB + um.off_off + (long long)((um.T - 1 - t) / kRenorm) * nthr;
+  const double lp2 = d.logp2[b];
   float *sm = gsm + wi * smem_pitch;
   float z = 0.f;
   for (int s = lane; s < S; s += 32) {
     const float ee = (s & 1) ? e[1 + (s >> 1)] : e[0];
-    const float v = exp2f(fmaxf(al[s] + be[s] - ee + D, -200.f));
+    const float cab = oa[(s >> 1) / P] + ob[(L - ((s + 1) >> 1)) / P];  // exact: integers
+    const float D = (float)((double)cab - lp2);
+    const float v = exp2f(fmaxf((al[s] + be[s] - ee) + D, -200.f));
     sm[s] = v;
     z += v;
   }
@@ -495,7 +517,7 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int A,
   p->maxL = 0;
   p->sumT = p->sumL = 0;
   p->meta.assign(B, UttMeta());
-  long long e_off = 0, ab_off = 0;
+  long long e_off = 0, ab_off = 0, off_off = 0;
   for (int b = 0; b < B; b++) {
     const int T = input_lengths[b], L = label_lengths[b];
     if (T <= 0 || L < 0) return CTC_STATUS_INVALID_VALUE;
@@ -507,7 +529,8 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int A,
     m.csr_off = (int)p->sumL;
     m.e_off = e_off;
     m.ab_off = ab_off;
-    m.fr_off = p->sumT;
+    m.off_off = off_off;
+    off_off += (long long)((T + kRenorm - 1) / kRenorm) * (L + 1);
     e_off += (long long)T * m.pitch;
     ab_off += (long long)T * 2 * m.pitch;
     p->sumT += T;
@@ -528,8 +551,8 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int A,
   p->off_E = o;      o = align_up(o + sizeof(float) * (size_t)e_off, 256);
   p->off_alpha = o;  o = align_up(o + sizeof(float) * (size_t)ab_off, 256);
   p->off_beta = o;   o = align_up(o + sizeof(float) * (size_t)ab_off, 256);
-  p->off_offA = o;   o = align_up(o + sizeof(double) * (size_t)p->sumT, 256);
-  p->off_offB = o;   o = align_up(o + sizeof(double) * (size_t)p->sumT, 256);
+  p->off_offA = o;   o = align_up(o + sizeof(float) * (size_t)off_off, 256);
+  p->off_offB = o;   o = align_up(o + sizeof(float) * (size_t)off_off, 256);
   p->off_logp2 = o;  o = align_up(o + sizeof(double) * 2 * B, 256);
   p->off_costs = o;  o = align_up(o + sizeof(float) * B, 256);
   p->off_flags = o;  o = align_up(o + 256, 256);
@@ -568,7 +591,7 @@ bool ensure_pinned(Staging &s, size_t bytes, size_t ncosts) {
 
 template <int P>
 cudaError_t launch_k2(const CtcDev &dev, int B, int NT, int F, cudaStream_t stream) {
-  const size_t smem = 1024 + sizeof(float) * 2 * kStages * kStageFloats;
+  const size_t smem = 2048 + sizeof(float) * 2 * kStages * kStageFloats;
   cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_kernel<P>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -650,20 +673,21 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   dev.E = reinterpret_cast<float *>(w + p.off_E);
   dev.alpha = reinterpret_cast<float *>(w + p.off_alpha);
   dev.beta = reinterpret_cast<float *>(w + p.off_beta);
-  dev.offA = reinterpret_cast<double *>(w + p.off_offA);
-  dev.offB = reinterpret_cast<double *>(w + p.off_offB);
+  dev.offA = reinterpret_cast<float *>(w + p.off_offA);
+  dev.offB = reinterpret_cast<float *>(w + p.off_offB);
   dev.logp2 = reinterpret_cast<double *>(w + p.off_logp2);
   dev.costs = reinterpret_cast<float *>(w + p.off_costs);
   dev.flags = reinterpret_cast<int *>(w + p.off_flags);
 
+  // K2 geometry: P pairs per thread so that one direction fits 512 threads
+  const int npairs = p.maxL + 1;
+  const int P = npairs <= 512 ? 1 : (npairs <= 1024 ? 2 : 4);
+  dev.P = P;
   const long long rows = (long long)p.Tmax * B;
   const unsigned g1 = (unsigned)((rows + kK1Warps - 1) / kK1Warps);
   ctc_rowstats_gather_kernel<<<g1, kK1Warps * 32, 0, stream>>>(dev);
   if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
 
-  // K2 geometry: P pairs per thread so that one direction fits 512 threads
-  const int npairs = p.maxL + 1;
-  const int P = npairs <= 512 ? 1 : (npairs <= 1024 ? 2 : 4);
   const int NT = (int)align_up((size_t)(npairs + P - 1) / P, 32);
   const int F = std::max(1, std::min(32, kStageFloats / p.pitch_max));
   cudaError_t ce = P == 1   ? launch_k2<1>(dev, B, NT, F, stream)
