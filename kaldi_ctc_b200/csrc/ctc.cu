@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int f
     }
     // end of a frame block: publish the offset the block was stored with, re-centre
     if ((step % kRenorm) == kRenorm - 1 || step == T - 1) {
-      off_out[(step / kRenorm) * nthreads_needed + r] = c;
+      if (r < nthreads_needed) off_out[(step / kRenorm) * nthreads_needed + r] = c;
       if (mx > -1.0e29f) {
         const float sh = floorf(mx);
 #pragma unroll
@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(kK3Warps * 32) ctc_grad_kernel(CtcDev d, int s
     const float ee = (s & 1) ? e[1 + (s >> 1)] : e[0];
     const float cab = oa[(s >> 1) / P] + ob[(L - ((s + 1) >> 1)) / P];  // exact: integers
     const float D = (float)((double)cab - lp2);
-    const float v = exp2f(fmaxf((al[s] + be[s] - ee) + D, -200.f));
+    const float v = exp2f(fminf(fmaxf((al[s] + be[s] - ee) + D, -200.f), 100.f));
     sm[s] = v;
     z += v;
   }

@@ -1,0 +1,73 @@
+// kaldi_ctc_b200/csrc/rnn_common.cuh -- shared declarations of libb200rnn.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/b200rnn.h"
+
+namespace b200 {
+
+inline __host__ __device__ int gates_of(int mode) { return mode == 2 ? 4 : (mode == 3 ? 3 : 1); }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// One pseudo-layer (layer, direction) of the packed blob; float offsets.
+struct PseudoLayer {
+  size_t w_in;   // [G*H x Din]  the G input matrices are contiguous
+  size_t w_rec;  // [G*H x H]
+  size_t b_in;   // [G*H]
+  size_t b_rec;  // [G*H]
+  int din;
+};
+
+// ------------------------------------------------------------------------
+// fp32 GEMM (rnn_gemm.cu):  C[MxN] = alpha * A(MxK) * B(KxN) + beta * C + bias
+// element (m,k) of A at A[m*sam + k*sak]; (k,n) of B at B[k*sbk + n*sbn].
+// splits > 1: K is cut in `splits` ranges, partial products go through
+// `partial` ([splits][M][N] floats) and are summed in a fixed order.
+// bias (nullable) is bias_a[n] + (n < nb ? bias_b[n] : 0).
+// ------------------------------------------------------------------------
+struct GemmArgs {
+  int M, N, K;
+  float alpha, beta;
+  const float *A;
+  long long sam, sak;
+  const float *B;
+  long long sbk, sbn;
+  float *C;
+  int ldc;
+  const float *bias_a, *bias_b;
+  int nb;
+  int splits;
+  float *partial;
+};
+cudaError_t gemm_fp32(const GemmArgs &g, cudaStream_t stream, int *launches);
+cudaError_t column_sums(const float *a, int rows, int cols, int lda, float *out, int accumulate,
+                        float *partial, size_t partial_floats, cudaStream_t stream, int *launches);
+size_t column_sums_partial_floats(int rows, int cols);
+
+// ------------------------------------------------------------------------
+// recurrent kernels, fp32 math (rnn_rec_fp32.cu)
+// ------------------------------------------------------------------------
+struct RecArgs {
+  int mode, T, B, H, dirs;
+  int NC;        // CTAs per cluster (one cluster per direction and batch chunk)
+  int U;         // hidden units per CTA = H / NC
+  int BC;        // batch chunk (<= 16)
+  const float *w_rec[2];  // [G*H x H]
+  const float *b_rec[2];  // [G*H]   (GRU: the n-gate part is applied inside)
+  float *gates[2];        // [T*B x G*H] fwd: pre-activations in, activations out
+                          //             bwd: activations in, input-side gate gradients out
+  float *cell[2];         // [T*B x H]   LSTM c_t / GRU q_t (bwd: GRU dq_t out)
+  float *y;               // [T*B x H*dirs]
+  const float *dy;        // bwd only
+  int save;               // fwd: 1 = keep activations/cell for backward
+};
+// smem bytes for a given geometry (0 = does not fit the fp32 persistent kernels)
+size_t rec_fp32_smem_bytes(int mode, int H, int NC, bool backward);
+cudaError_t rec_fp32_forward(const RecArgs &a, cudaStream_t stream);
+cudaError_t rec_fp32_backward(const RecArgs &a, cudaStream_t stream);
+// largest usable cluster size for this geometry (0 if none), probing the device
+int rec_fp32_pick_cluster(int mode, int H);
+
+}  // namespace b200
