@@ -118,10 +118,13 @@ b200rnnStatus_t b200rnnClipRowNorm(float *d, int rows, int cols, float threshold
 /* Plain row-major fp32 GEMM used for the adjacent AffineComponent
  * (src/nnet2/nnet-component.cc:1184-1226): C[M x N] = alpha*op(A)*op(B) + beta*C
  * (+ bias[n] broadcast over rows when bias != NULL).  trans: 0 = as stored
- * [rows x cols], 1 = transposed.  math selects FP32 or TF32-tcgen05. */
+ * [rows x cols], 1 = transposed.  math selects FP32 or TF32-tcgen05.  An optional
+ * DEVICE workspace enables a deterministic split-K for short-and-wide products
+ * (weight gradients); NULL / 0 is always valid. */
 b200rnnStatus_t b200rnnGemm(int transA, int transB, int M, int N, int K, float alpha,
                             const float *A, int lda, const float *B, int ldb, float beta, float *C,
-                            int ldc, const float *bias, b200rnnMath_t math, b200rnnStream_t stream);
+                            int ldc, const float *bias, b200rnnMath_t math, void *workspace,
+                            size_t workspace_bytes, b200rnnStream_t stream);
 
 /* Column sums: out[c] (+)= sum_r a[r, c]  (AffineComponent bias gradient). */
 b200rnnStatus_t b200rnnColumnSums(const float *a, int rows, int cols, int lda, float *out,

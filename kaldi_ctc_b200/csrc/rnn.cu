@@ -1,0 +1,432 @@
+// kaldi_ctc_b200/csrc/rnn.cu -- C ABI of libb200rnn.so (include/b200rnn.h):
+// plan, blob layout, workspace/reserve carving and the per-layer orchestration
+// of forward / backward-data / backward-weights.  Replaces what
+// CuDNNRecurrentComponent gets from cuDNN 5 (src/nnet2/nnet-cudnn-component.cc
+// :100-315 descriptors, :534-555 forward, :576-599 backward).
+#include <stdio.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "rnn_common.cuh"
+
+using namespace b200;
+
+struct b200rnnPlan_st {
+  int mode, dirs, layers, D, H, B, Tmax, math;
+  int G, GH, HO;
+  std::vector<PseudoLayer> pl;
+  size_t param_count;
+  // recurrent-kernel geometry, probed on first use (needs the device)
+  int NC, BC;
+  bool geometry_ready;
+  int launches;
+  // reserve layout (floats), per layer
+  std::vector<size_t> r_gates[2], r_cell[2], r_y;
+  size_t reserve_floats;
+  // workspace layout (floats)
+  size_t w_colsum, w_splitk, w_pp[2], w_gates[2], workspace_floats;
+  size_t splitk_floats, colsum_floats;
+};
+
+namespace {
+
+constexpr int kSplitK = 16;
+
+int din_of(const b200rnnPlan_st *p, int layer) { return layer == 0 ? p->D : p->HO; }
+
+b200rnnStatus_t ensure_geometry(b200rnnPlan_st *p) {
+  if (p->geometry_ready) return B200RNN_STATUS_SUCCESS;
+  p->NC = rec_fp32_pick_cluster(p->mode, p->H);
+  if (p->NC == 0) return B200RNN_STATUS_NOT_SUPPORTED;
+  p->BC = 16;
+  p->geometry_ready = true;
+  return B200RNN_STATUS_SUCCESS;
+}
+
+__global__ void clip_update_kernel(float *w, const float *dw, size_t n, float lr, float clip) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float g = dw[i];
+    if (clip > 0.f) g = fminf(fmaxf(g, -clip), clip);
+    w[i] = fmaf(lr, g, w[i]);
+  }
+}
+
+// one warp per row: scale rows whose L2 norm exceeds thr down to thr
+__global__ void clip_row_norm_kernel(float *d, int rows, int cols, float thr) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float *p = d + (size_t)row * cols;
+  float ss = 0.f;
+  for (int c = lane; c < cols; c += 32) ss = fmaf(p[c], p[c], ss);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float r = ss / (thr * thr);
+  if (r > 1.0f) {
+    const float sc = rsqrtf(r);
+    for (int c = lane; c < cols; c += 32) p[c] *= sc;
+  }
+}
+
+b200rnnStatus_t to_status(cudaError_t e) {
+  if (e == cudaSuccess) return B200RNN_STATUS_SUCCESS;
+  fprintf(stderr, "b200rnn: CUDA error: %s\n", cudaGetErrorString(e));
+  return B200RNN_STATUS_EXECUTION_FAILED;
+}
+
+#define CK(expr)                                   \
+  do {                                             \
+    cudaError_t e__ = (expr);                      \
+    if (e__ != cudaSuccess) return to_status(e__); \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+const char *b200rnnGetStatusString(b200rnnStatus_t s) {
+  switch (s) {
+    case B200RNN_STATUS_SUCCESS: return "success";
+    case B200RNN_STATUS_INVALID_VALUE: return "invalid value";
+    case B200RNN_STATUS_ALLOC_FAILED: return "allocation failed";
+    case B200RNN_STATUS_EXECUTION_FAILED: return "execution failed";
+    case B200RNN_STATUS_NOT_SUPPORTED: return "configuration not supported";
+    default: return "unknown status";
+  }
+}
+
+b200rnnStatus_t b200rnnCreatePlan(b200rnnPlan_t *plan, b200rnnMode_t mode, int bidirectional,
+                                  int num_layers, int input_dim, int hidden_dim, int minibatch,
+                                  int max_seq_length, b200rnnMath_t math) {
+  if (!plan || (int)mode < 0 || (int)mode > 3 || num_layers < 1 || input_dim < 1 ||
+      hidden_dim < 1 || minibatch < 1 || max_seq_length < 1 || (int)math < 0 || (int)math > 1)
+    return B200RNN_STATUS_INVALID_VALUE;
+  b200rnnPlan_st *p = new (std::nothrow) b200rnnPlan_st();
+  if (!p) return B200RNN_STATUS_ALLOC_FAILED;
+  p->mode = mode;
+  p->dirs = bidirectional ? 2 : 1;
+  p->layers = num_layers;
+  p->D = input_dim;
+  p->H = hidden_dim;
+  p->B = minibatch;
+  p->Tmax = max_seq_length;
+  p->math = math;
+  p->G = gates_of(mode);
+  p->GH = p->G * p->H;
+  p->HO = p->H * p->dirs;
+  p->geometry_ready = false;
+  p->NC = p->BC = 0;
+  p->launches = 0;
+  // blob: all matrices of all pseudo-layers, then all biases
+  const int npl = p->layers * p->dirs;
+  p->pl.resize(npl);
+  size_t off = 0;
+  for (int q = 0; q < npl; q++) {
+    const int din = din_of(p, q / p->dirs);
+    p->pl[q].din = din;
+    p->pl[q].w_in = off;
+    off += (size_t)p->GH * din;
+    p->pl[q].w_rec = off;
+    off += (size_t)p->GH * p->H;
+  }
+  for (int q = 0; q < npl; q++) {
+    p->pl[q].b_in = off;
+    off += p->GH;
+    p->pl[q].b_rec = off;
+    off += p->GH;
+  }
+  p->param_count = off;
+  // reserve
+  const size_t TB = (size_t)p->Tmax * p->B;
+  size_t r = 0;
+  for (int d = 0; d < 2; d++) {
+    p->r_gates[d].assign(p->layers, 0);
+    p->r_cell[d].assign(p->layers, 0);
+  }
+  p->r_y.assign(p->layers, 0);
+  for (int l = 0; l < p->layers; l++) {
+    for (int d = 0; d < p->dirs; d++) {
+      p->r_gates[d][l] = r;
+      r = align_up(r + TB * p->GH, 64);
+      p->r_cell[d][l] = r;
+      r = align_up(r + TB * p->H, 64);
+    }
+    if (l + 1 < p->layers) {
+      p->r_y[l] = r;
+      r = align_up(r + TB * p->HO, 64);
+    }
+  }
+  p->reserve_floats = r;
+  // workspace
+  size_t w = 0;
+  p->colsum_floats = column_sums_partial_floats((int)TB, p->GH);
+  p->w_colsum = w;
+  w = align_up(w + p->colsum_floats, 64);
+  const int maxin = std::max(std::max(p->D, p->HO), p->H);
+  p->splitk_floats = (size_t)kSplitK * p->GH * maxin;
+  p->w_splitk = w;
+  w = align_up(w + p->splitk_floats, 64);
+  for (int i = 0; i < 2; i++) {
+    p->w_pp[i] = w;
+    if (p->layers > 1) w = align_up(w + TB * p->HO, 64);
+  }
+  for (int d = 0; d < p->dirs; d++) {
+    p->w_gates[d] = w;
+    w = align_up(w + TB * p->GH, 64);
+  }
+  p->workspace_floats = w;
+  *plan = p;
+  return B200RNN_STATUS_SUCCESS;
+}
+
+b200rnnStatus_t b200rnnDestroyPlan(b200rnnPlan_t plan) {
+  delete plan;
+  return B200RNN_STATUS_SUCCESS;
+}
+
+b200rnnStatus_t b200rnnGetParamCount(b200rnnPlan_t p, size_t *count) {
+  if (!p || !count) return B200RNN_STATUS_INVALID_VALUE;
+  *count = p->param_count;
+  return B200RNN_STATUS_SUCCESS;
+}
+
+b200rnnStatus_t b200rnnLocateParam(b200rnnPlan_t p, int pseudo_layer, int lin_id, int is_bias,
+                                   size_t *offset, int *rows, int *cols) {
+  if (!p || !offset || !rows || !cols) return B200RNN_STATUS_INVALID_VALUE;
+  if (pseudo_layer < 0 || pseudo_layer >= p->layers * p->dirs || lin_id < 0 || lin_id >= 2 * p->G)
+    return B200RNN_STATUS_INVALID_VALUE;
+  const PseudoLayer &q = p->pl[pseudo_layer];
+  const bool rec = lin_id >= p->G;
+  const int g = rec ? lin_id - p->G : lin_id;
+  *rows = p->H;
+  if (is_bias) {
+    *offset = (rec ? q.b_rec : q.b_in) + (size_t)g * p->H;
+    *cols = 1;
+  } else {
+    const int in = rec ? p->H : q.din;
+    *offset = (rec ? q.w_rec : q.w_in) + (size_t)g * p->H * in;
+    *cols = in;
+  }
+  return B200RNN_STATUS_SUCCESS;
+}
+
+b200rnnStatus_t b200rnnGetWorkspaceSize(b200rnnPlan_t p, size_t *bytes) {
+  if (!p || !bytes) return B200RNN_STATUS_INVALID_VALUE;
+  *bytes = p->workspace_floats * sizeof(float);
+  return B200RNN_STATUS_SUCCESS;
+}
+
+b200rnnStatus_t b200rnnGetReserveSize(b200rnnPlan_t p, size_t *bytes) {
+  if (!p || !bytes) return B200RNN_STATUS_INVALID_VALUE;
+  *bytes = p->reserve_floats * sizeof(float);
+  return B200RNN_STATUS_SUCCESS;
+}
+
+b200rnnStatus_t b200rnnForward(b200rnnPlan_t p, int T, const float *x, const float *w, float *y,
+                               void *workspace, void *reserve, b200rnnStream_t stream_) {
+  if (!p || !x || !w || !y || !workspace || T < 1 || T > p->Tmax) return B200RNN_STATUS_INVALID_VALUE;
+  b200rnnStatus_t gs = ensure_geometry(p);
+  if (gs != B200RNN_STATUS_SUCCESS) return gs;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  float *ws = static_cast<float *>(workspace), *rs = static_cast<float *>(reserve);
+  const int TB = T * p->B;
+  p->launches = 0;
+  for (int l = 0; l < p->layers; l++) {
+    const int din = din_of(p, l);
+    const float *in = l == 0 ? x : (rs ? rs + p->r_y[l - 1] : ws + p->w_pp[(l - 1) & 1]);
+    float *out = l == p->layers - 1 ? y : (rs ? rs + p->r_y[l] : ws + p->w_pp[l & 1]);
+    RecArgs a = {};
+    a.mode = p->mode; a.T = T; a.B = p->B; a.H = p->H; a.dirs = p->dirs;
+    a.NC = p->NC; a.U = p->H / p->NC; a.BC = p->BC;
+    a.y = out; a.dy = nullptr; a.save = rs ? 1 : 0;
+    for (int d = 0; d < p->dirs; d++) {
+      const PseudoLayer &q = p->pl[l * p->dirs + d];
+      float *gates = rs ? rs + p->r_gates[d][l] : ws + p->w_gates[d];
+      // hoisted input projection with both biases folded in (GRU: recurrent n-bias stays inside)
+      GemmArgs g = {};
+      g.M = TB; g.N = p->GH; g.K = din; g.alpha = 1.f; g.beta = 0.f;
+      g.A = in; g.sam = din; g.sak = 1;
+      g.B = w + q.w_in; g.sbk = 1; g.sbn = din;
+      g.C = gates; g.ldc = p->GH;
+      g.bias_a = w + q.b_in; g.bias_b = w + q.b_rec;
+      g.nb = p->mode == 3 ? 2 * p->H : p->GH;
+      g.splits = 1; g.partial = nullptr;
+      CK(gemm_fp32(g, stream, &p->launches));
+      a.w_rec[d] = w + q.w_rec;
+      a.b_rec[d] = w + q.b_rec;
+      a.gates[d] = gates;
+      a.cell[d] = rs ? rs + p->r_cell[d][l] : nullptr;
+    }
+    CK(rec_fp32_forward(a, stream));
+    p->launches++;
+  }
+  return B200RNN_STATUS_SUCCESS;
+}
+
+b200rnnStatus_t b200rnnBackwardData(b200rnnPlan_t p, int T, const float *y, const float *dy,
+                                    const float *w, float *dx, void *workspace, void *reserve,
+                                    b200rnnStream_t stream_) {
+  if (!p || !y || !dy || !w || !workspace || !reserve || T < 1 || T > p->Tmax)
+    return B200RNN_STATUS_INVALID_VALUE;
+  b200rnnStatus_t gs = ensure_geometry(p);
+  if (gs != B200RNN_STATUS_SUCCESS) return gs;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  float *ws = static_cast<float *>(workspace), *rs = static_cast<float *>(reserve);
+  const int TB = T * p->B;
+  p->launches = 0;
+  for (int l = p->layers - 1; l >= 0; l--) {
+    const int din = din_of(p, l);
+    const float *yl = l == p->layers - 1 ? y : rs + p->r_y[l];
+    const float *dyl = l == p->layers - 1 ? dy : ws + p->w_pp[l & 1];
+    float *dxl = l == 0 ? dx : ws + p->w_pp[(l - 1) & 1];
+    RecArgs a = {};
+    a.mode = p->mode; a.T = T; a.B = p->B; a.H = p->H; a.dirs = p->dirs;
+    a.NC = p->NC; a.U = p->H / p->NC; a.BC = p->BC;
+    a.y = const_cast<float *>(yl); a.dy = dyl; a.save = 1;
+    for (int d = 0; d < p->dirs; d++) {
+      const PseudoLayer &q = p->pl[l * p->dirs + d];
+      a.w_rec[d] = w + q.w_rec;
+      a.b_rec[d] = w + q.b_rec;
+      a.gates[d] = rs + p->r_gates[d][l];
+      a.cell[d] = rs + p->r_cell[d][l];
+    }
+    CK(rec_fp32_backward(a, stream));
+    p->launches++;
+    if (dxl) {
+      for (int d = 0; d < p->dirs; d++) {
+        const PseudoLayer &q = p->pl[l * p->dirs + d];
+        GemmArgs g = {};
+        g.M = TB; g.N = din; g.K = p->GH; g.alpha = 1.f; g.beta = d == 0 ? 0.f : 1.f;
+        g.A = rs + p->r_gates[d][l]; g.sam = p->GH; g.sak = 1;
+        g.B = w + q.w_in; g.sbk = din; g.sbn = 1;
+        g.C = dxl; g.ldc = din;
+        g.splits = 1;
+        CK(gemm_fp32(g, stream, &p->launches));
+      }
+    }
+  }
+  return B200RNN_STATUS_SUCCESS;
+}
+
+b200rnnStatus_t b200rnnBackwardWeights(b200rnnPlan_t p, int T, const float *x, const float *y,
+                                       float *dw, void *workspace, void *reserve,
+                                       b200rnnStream_t stream_) {
+  if (!p || !x || !y || !dw || !workspace || !reserve || T < 1 || T > p->Tmax)
+    return B200RNN_STATUS_INVALID_VALUE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  float *ws = static_cast<float *>(workspace), *rs = static_cast<float *>(reserve);
+  const int TB = T * p->B, B = p->B, H = p->H, GH = p->GH, HO = p->HO;
+  p->launches = 0;
+  for (int l = 0; l < p->layers; l++) {
+    const int din = din_of(p, l);
+    const float *in = l == 0 ? x : rs + p->r_y[l - 1];
+    const float *yl = l == p->layers - 1 ? y : rs + p->r_y[l];
+    for (int d = 0; d < p->dirs; d++) {
+      const PseudoLayer &q = p->pl[l * p->dirs + d];
+      const float *dg = rs + p->r_gates[d][l];
+      const float *dq = rs + p->r_cell[d][l];
+      // dWi += dG^T . in          [GH x din], K = T*B
+      GemmArgs g = {};
+      g.M = GH; g.N = din; g.K = TB; g.alpha = 1.f; g.beta = 1.f;
+      g.A = dg; g.sam = 1; g.sak = GH;
+      g.B = in; g.sbk = din; g.sbn = 1;
+      g.C = dw + q.w_in; g.ldc = din;
+      g.splits = kSplitK; g.partial = ws + p->w_splitk;
+      CK(gemm_fp32(g, stream, &p->launches));
+      // dR += dGrec^T . h_prev    h_prev(t) = y(t -+ 1): a row shift of B
+      if (T > 1) {
+        const int K = (T - 1) * B;
+        const size_t sh_g = d == 0 ? (size_t)B : 0, sh_y = d == 0 ? 0 : (size_t)B;
+        GemmArgs r = {};
+        r.N = H; r.K = K; r.alpha = 1.f; r.beta = 1.f;
+        r.B = yl + sh_y * HO + (size_t)d * H; r.sbk = HO; r.sbn = 1;
+        r.ldc = H; r.splits = kSplitK; r.partial = ws + p->w_splitk;
+        r.M = p->mode == 3 ? 2 * H : GH;
+        r.A = dg + sh_g * GH; r.sam = 1; r.sak = GH;
+        r.C = dw + q.w_rec;
+        CK(gemm_fp32(r, stream, &p->launches));
+        if (p->mode == 3) {  // n-gate: recurrent-side gradient lives in the cell buffer
+          r.M = H;
+          r.A = dq + sh_g * H; r.sam = 1; r.sak = H;
+          r.C = dw + q.w_rec + (size_t)2 * H * H;
+          CK(gemm_fp32(r, stream, &p->launches));
+        }
+      }
+      // biases
+      float *part = ws + p->w_colsum;
+      CK(column_sums(dg, TB, GH, GH, dw + q.b_in, 1, part, p->colsum_floats, stream, &p->launches));
+      if (p->mode == 3) {
+        CK(column_sums(dg, TB, 2 * H, GH, dw + q.b_rec, 1, part, p->colsum_floats, stream, &p->launches));
+        CK(column_sums(dq, TB, H, H, dw + q.b_rec + 2 * H, 1, part, p->colsum_floats, stream, &p->launches));
+      } else {
+        CK(column_sums(dg, TB, GH, GH, dw + q.b_rec, 1, part, p->colsum_floats, stream, &p->launches));
+      }
+    }
+  }
+  return B200RNN_STATUS_SUCCESS;
+}
+
+b200rnnStatus_t b200rnnClipAndUpdate(float *w, const float *dw, size_t n, float lr, float clip,
+                                     b200rnnStream_t stream) {
+  if (!w || !dw) return B200RNN_STATUS_INVALID_VALUE;
+  if (n == 0) return B200RNN_STATUS_SUCCESS;
+  const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
+  clip_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, dw, n, lr, clip);
+  return to_status(cudaGetLastError());
+}
+
+b200rnnStatus_t b200rnnClipRowNorm(float *d, int rows, int cols, float threshold,
+                                   b200rnnStream_t stream) {
+  if (!d || rows < 0 || cols < 1 || threshold <= 0.f) return B200RNN_STATUS_INVALID_VALUE;
+  if (rows == 0) return B200RNN_STATUS_SUCCESS;
+  clip_row_norm_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(d, rows, cols, threshold);
+  return to_status(cudaGetLastError());
+}
+
+b200rnnStatus_t b200rnnGemm(int transA, int transB, int M, int N, int K, float alpha,
+                            const float *A, int lda, const float *B, int ldb, float beta, float *C,
+                            int ldc, const float *bias, b200rnnMath_t math, void *workspace,
+                            size_t workspace_bytes, b200rnnStream_t stream) {
+  if (!A || !B || !C || M < 0 || N < 0 || K < 0) return B200RNN_STATUS_INVALID_VALUE;
+  (void)math;
+  GemmArgs g = {};
+  g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta;
+  g.A = A; g.sam = transA ? 1 : lda; g.sak = transA ? lda : 1;
+  g.B = B; g.sbk = transB ? 1 : ldb; g.sbn = transB ? ldb : 1;
+  g.C = C; g.ldc = ldc; g.bias_a = bias; g.bias_b = nullptr; g.nb = 0;
+  g.splits = 1; g.partial = nullptr;
+  if (workspace && (size_t)M * N > 0) {
+    const size_t per = (size_t)M * N * sizeof(float);
+    int s = (int)std::min<size_t>(workspace_bytes / per, 32);
+    const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+    if (s >= 2 && tiles < 148 && K >= 4096) {
+      g.splits = std::min(s, std::max(2, 296 / std::max(tiles, 1)));
+      g.partial = static_cast<float *>(workspace);
+    }
+  }
+  return to_status(gemm_fp32(g, (cudaStream_t)stream, nullptr));
+}
+
+b200rnnStatus_t b200rnnColumnSums(const float *a, int rows, int cols, int lda, float *out,
+                                  int accumulate, void *workspace, size_t workspace_bytes,
+                                  b200rnnStream_t stream) {
+  if (!a || !out || !workspace) return B200RNN_STATUS_INVALID_VALUE;
+  cudaError_t e = column_sums(a, rows, cols, lda, out, accumulate, static_cast<float *>(workspace),
+                              workspace_bytes / sizeof(float), (cudaStream_t)stream, nullptr);
+  return e == cudaErrorInvalidValue ? B200RNN_STATUS_INVALID_VALUE : to_status(e);
+}
+
+double b200rnnForwardFlops(b200rnnPlan_t p, int T) {
+  if (!p) return 0.0;
+  double per = 0.0;
+  for (int l = 0; l < p->layers; l++)
+    per += (double)p->dirs * 2.0 * p->GH * ((double)din_of(p, l) + p->H);
+  return per * T * p->B;
+}
+
+int b200rnnLastLaunchCount(b200rnnPlan_t p) { return p ? p->launches : 0; }
+
+}  // extern "C"

@@ -120,7 +120,10 @@ if __name__ == "__main__":
     ctc_case("ctc_wide", B=3, A=500, t_lo=30, t_hi=60, l_lo=3, l_hi=14, seed=15, sigma=2.0)
     rnn_case("rnn_lstm_bi", 2, True, 1, 7, 12, 3, 6, 21)
     rnn_case("rnn_lstm_uni2", 2, False, 2, 5, 8, 2, 5, 22)
-    rnn_case("rnn_gru_bi", 3, True, 1, 6, 10, 3, 7, 23)
-    rnn_case("rnn_gru_bi2", 3, True, 2, 4, 6, 2, 5, 24)
-    rnn_case("rnn_relu_bi", 0, True, 1, 5, 9, 2, 6, 25)
-    rnn_case("rnn_tanh_uni", 1, False, 1, 5, 9, 2, 6, 26)
+    rnn_case("rnn_gru_bi", 3, True, 1, 6, 12, 3, 7, 23)
+    rnn_case("rnn_gru_bi2", 3, True, 2, 4, 8, 2, 5, 24)
+    rnn_case("rnn_relu_bi", 0, True, 1, 5, 12, 2, 6, 25)
+    rnn_case("rnn_tanh_uni", 1, False, 1, 5, 8, 2, 6, 26)
+    # odd hidden sizes (no divisibility by 4): exercised once the generic path exists
+    rnn_case("rnn_gru_odd", 3, True, 1, 6, 10, 3, 7, 27)
+    rnn_case("rnn_lstm_odd", 2, True, 1, 5, 9, 2, 6, 28)

@@ -9,7 +9,7 @@ import pytest
 
 from oracle import pyoracle
 
-CASES = ["rnn_lstm_bi", "rnn_lstm_uni2", "rnn_gru_bi", "rnn_gru_bi2", "rnn_relu_bi", "rnn_tanh_uni"]
+CASES = ["rnn_lstm_bi", "rnn_lstm_uni2", "rnn_gru_bi", "rnn_gru_bi2", "rnn_relu_bi", "rnn_tanh_uni", "rnn_gru_odd", "rnn_lstm_odd"]
 
 
 def _load(golden_dir, name):
