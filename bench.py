@@ -1,0 +1,249 @@
+#!/usr/bin/env python
+"""bench.py -- BLSTM+CTC training frames/s (BASELINE.json metric) on N B200s.
+
+A "step" is one NnetCtcUpdater::ComputeForMinibatch (src/ctc/ctc-nnet-update.cc:94-127)
+on one synthetic minibatch of the workload BASELINE.json quotes the metric on
+(configs[1]: 5 x BLSTM-320, 40-dim input, 48 outputs, minibatch 16, T_b ~ U{1200..2000}):
+forward, CTC loss + gradient, backward, weight update.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--math fp32|tensor]
+  python bench.py --impl reference ...      # CPU restatement of the reference's path
+Under torchrun (N > 1) every rank takes its own 16 utterances (weak scaling,
+utterance-sharded as SURVEY.md 8(e)); weight gradients are summed with NCCL
+all-reduce before the clip-and-update.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "blstm_ctc_train_frames_per_sec"
+UNIT = "frames/s"
+WORKLOAD = "configs[1]: cudnn_google 5xBLSTM-320 (D=40) + affine 640->48 + CTC, minibatch 16/GPU, T_b~U{1200..2000}, L_b~U{120..180}"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples = index, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [v.strip() for v in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        mhz = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def make_workload(spec, rank, B=16, t_lo=1200, t_hi=2000):
+    from kaldi_ctc_b200 import synth
+    x, fl, L, T = synth.features(B, spec.D, t_lo, t_hi, 120, 180, spec.A, seed=1002 + 97 * rank)
+    return x, fl, L, T
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU path, restated (oracle/): timed on this box's host cores."""
+    if rank != 0:
+        return
+    from kaldi_ctc_b200 import synth
+    from oracle import pymodel, pyoracle
+    pyoracle.build()
+    spec = synth.ModelSpec()
+    blobs, aw, ab = synth.model_weights(spec, 7)
+    B, Ts = 16, args.ref_frames
+    x, fl, L, T = synth.features(B, spec.D, Ts, Ts, max(1, Ts // 12), max(2, Ts // 8), spec.A, seed=1002)
+    cores = os.cpu_count() or 1
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        pymodel.train_step(spec, blobs, aw, ab, x, fl, L, T, B, dtype=np.float32, num_threads=cores)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    value = float(T.sum()) / (ms / 1e3)
+    sample = "%d utts x %d frames of the same 5xBLSTM-320+CTC step per step (fp32, OpenMP)" % (B, Ts)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def cpu_baseline(spec, blobs, aw, ab, frames=96):
+    from kaldi_ctc_b200 import synth
+    from oracle import pymodel
+    B = 16
+    x, fl, L, T = synth.features(B, spec.D, frames, frames, max(1, frames // 12), max(2, frames // 8), spec.A, seed=1002)
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    pymodel.train_step(spec, blobs, aw, ab, x, fl, L, T, B, dtype=np.float32, num_threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": float(T.sum()) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "1 step of %d utts x %d frames (same model, fp32 OpenMP restatement)" % (B, frames)}
+
+
+def run_b200(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from kaldi_ctc_b200 import nnet, rnn, synth
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = "cuda:%d" % local_rank
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    math = rnn.MATH_TENSOR if args.math == "tensor" else rnn.MATH_FP32
+    spec = synth.ModelSpec()
+    blobs, aw, ab = synth.model_weights(spec, 7)        # same initial model on every rank
+    x, fl, L, T = make_workload(spec, rank)
+    B, Tmax = 16, int(T.max())
+    up = nnet.NnetCtcUpdater(spec, blobs, aw, ab, B, Tmax, device=dev, math=math, world=world)
+    feats = torch.from_numpy(x).pin_memory()
+    valid_frames = int(T.sum())
+
+    def step(resident):
+        if resident:
+            return up.ComputeForMinibatch(None, Tmax, fl, L, T, host_sync=False)
+        return up.ComputeForMinibatch(feats, Tmax, fl, L, T, host_sync=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(resident, steps, profile=False):
+        for c in up.rnns:
+            c.plan.set_profiling(profile)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(resident)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    up.FormatInput(feats, Tmax)
+    for _ in range(args.warmup):
+        step(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_res = timed(True, args.steps, profile=True)
+    prof = [[c.plan.get_profile(k) for k in range(3)] for c in up.rnns]
+    sampler.stop_flag.set()
+    sampler.join()
+    ms_e2e = timed(False, args.steps)
+    objf = up.last_objf()
+
+    # ---- roofline of the dominant kernel (CUDA events recorded inside the timed region)
+    pk, pk_src = peaks()
+    cat_ms = [sum(p[k][0] for p in prof) for k in range(3)]
+    cat_n = [sum(p[k][1] for p in prof) for k in range(3)]
+    names = ["recurrent_forward", "recurrent_backward", "projection/gradient GEMMs"]
+    k = int(np.argmax(cat_ms))
+    G, H, dirs = 4, spec.H, 2
+    rec_flops_per_launch = dirs * 2.0 * G * H * H * Tmax * B            # per layer, padded frames are real work
+    gemm_flops_per_step = 0.0
+    for l in range(spec.layers):
+        din = spec.D if l == 0 else H * dirs
+        gemm_flops_per_step += dirs * 2.0 * G * H * Tmax * B * (din * (3 if l > 0 else 2) + H)
+    if k < 2:
+        flops_per_launch = rec_flops_per_launch
+    else:
+        flops_per_launch = gemm_flops_per_step * args.steps / max(cat_n[2], 1)
+    avg_s = cat_ms[k] / max(cat_n[k], 1) / 1e3
+    achieved = flops_per_launch / avg_s / 1e12 if avg_s > 0 else 0.0
+    peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    roofline = {"bound": "tensor", "kernel": names[k], "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": pk_src + " (bf16 sustained)",
+                "share_of_step": cat_ms[k] / ms_res,
+                "ms_per_step_by_kernel": {names[i]: cat_ms[i] / args.steps for i in range(3)}}
+
+    h2d = int(Tmax * B * spec.D * 4)
+    d2h = int(B * 4)
+    line = {
+        "metric": METRIC, "value": valid_frames * world * args.steps / (ms_res / 1e3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if math == rnn.MATH_FP32 else "tf32/bf16 tensor-core operands, f32 accumulate+state; CTC f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "math": args.math, "global_batch": B * world,
+                   "valid_frames_per_step": valid_frames * world, "padded_frames_per_step": Tmax * B * world,
+                   "parallelism": "dp%d (utterance-sharded, NCCL all-reduce of weight gradients)" % world,
+                   "l2": "working set per step (activations+reserve ~2.5 GB) >> 126 MB L2; no explicit flush"},
+        "e2e": {"value": valid_frames * world * args.steps / (ms_e2e / 1e3), "unit": UNIT,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": up.launches_per_step() * args.steps,
+        "clocks": sampler.summary(),
+        "roofline": roofline,
+        "objf_last_step": objf,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(spec, blobs, aw, ab)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--math", default=os.environ.get("B200_MATH", "fp32"), choices=["fp32", "tensor"])
+    ap.add_argument("--ref-frames", type=int, default=64, help="frames per utterance of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -126,14 +126,23 @@ b200rnnStatus_t b200rnnGemm(int transA, int transB, int M, int N, int K, float a
                             int ldc, const float *bias, b200rnnMath_t math, void *workspace,
                             size_t workspace_bytes, b200rnnStream_t stream);
 
-/* Column sums: out[c] (+)= sum_r a[r, c]  (AffineComponent bias gradient). */
-b200rnnStatus_t b200rnnColumnSums(const float *a, int rows, int cols, int lda, float *out,
-                                  int accumulate, void *workspace, size_t workspace_bytes,
-                                  b200rnnStream_t stream);
+/* Column sums: out[c] = (accumulate ? out[c] : 0) + alpha * sum_r a[r, c]
+ * (AffineComponent bias update: bias += lr * colsum(deriv)).  Deterministic. */
+b200rnnStatus_t b200rnnColumnSums(const float *a, int rows, int cols, int lda, float alpha,
+                                  float *out, int accumulate, void *workspace,
+                                  size_t workspace_bytes, b200rnnStream_t stream);
 
 /* FLOPs of one forward call at seq_length T (counting padded frames, as the
  * reference computes them): sum_layers dirs*2*ng*H*(D_l+H) per (frame, utt). */
 double b200rnnForwardFlops(b200rnnPlan_t plan, int seq_length);
+
+/* Optional CUDA-event timing of the kernels a plan launches (the reference times
+ * every cuDNN call into CuDevice::AccuProfile, src/cudamatrix/cudnn-recurrent.cc:25-30).
+ * Categories: 0 = recurrent forward kernel, 1 = recurrent backward kernel, 2 = GEMMs.
+ * GetProfile synchronises the recorded events, returns the sums since the previous
+ * GetProfile of that category and resets them. */
+b200rnnStatus_t b200rnnSetProfiling(b200rnnPlan_t plan, int enable);
+b200rnnStatus_t b200rnnGetProfile(b200rnnPlan_t plan, int category, float *total_ms, int *launches);
 
 /* Kernels launched by the last Forward / BackwardData / BackwardWeights call on
  * this plan (bench.py's gpu_launches bookkeeping). */

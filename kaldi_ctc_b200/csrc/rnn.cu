@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "rnn_common.cuh"
@@ -28,6 +29,10 @@ struct b200rnnPlan_st {
   // workspace layout (floats)
   size_t w_colsum, w_splitk, w_pp[2], w_gates[2], workspace_floats;
   size_t splitk_floats, colsum_floats;
+  // optional event timing: [category] -> recorded (start, stop) pairs
+  bool profiling;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];
+  size_t ev_used[3];
 };
 
 namespace {
@@ -77,6 +82,27 @@ b200rnnStatus_t to_status(cudaError_t e) {
   return B200RNN_STATUS_EXECUTION_FAILED;
 }
 
+struct Timed {  // records an event pair around a launch when profiling is on
+  b200rnnPlan_st *p;
+  int cat;
+  cudaStream_t s;
+  Timed(b200rnnPlan_st *p_, int cat_, cudaStream_t s_) : p(p_), cat(cat_), s(s_) {
+    if (!p->profiling) return;
+    if (p->ev_used[cat] == p->ev[cat].size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      p->ev[cat].push_back(std::make_pair(a, b));
+    }
+    cudaEventRecord(p->ev[cat][p->ev_used[cat]].first, s);
+  }
+  ~Timed() {
+    if (!p->profiling) return;
+    cudaEventRecord(p->ev[cat][p->ev_used[cat]].second, s);
+    p->ev_used[cat]++;
+  }
+};
+
 #define CK(expr)                                   \
   do {                                             \
     cudaError_t e__ = (expr);                      \
@@ -120,6 +146,8 @@ b200rnnStatus_t b200rnnCreatePlan(b200rnnPlan_t *plan, b200rnnMode_t mode, int b
   p->geometry_ready = false;
   p->NC = p->BC = 0;
   p->launches = 0;
+  p->profiling = false;
+  p->ev_used[0] = p->ev_used[1] = p->ev_used[2] = 0;
   // blob: all matrices of all pseudo-layers, then all biases
   const int npl = p->layers * p->dirs;
   p->pl.resize(npl);
@@ -183,6 +211,12 @@ b200rnnStatus_t b200rnnCreatePlan(b200rnnPlan_t *plan, b200rnnMode_t mode, int b
 }
 
 b200rnnStatus_t b200rnnDestroyPlan(b200rnnPlan_t plan) {
+  if (plan)
+    for (int c = 0; c < 3; c++)
+      for (auto &e : plan->ev[c]) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+      }
   delete plan;
   return B200RNN_STATUS_SUCCESS;
 }
@@ -254,13 +288,19 @@ b200rnnStatus_t b200rnnForward(b200rnnPlan_t p, int T, const float *x, const flo
       g.bias_a = w + q.b_in; g.bias_b = w + q.b_rec;
       g.nb = p->mode == 3 ? 2 * p->H : p->GH;
       g.splits = 1; g.partial = nullptr;
-      CK(gemm_fp32(g, stream, &p->launches));
+      {
+        Timed tm(p, 2, stream);
+        CK(gemm_fp32(g, stream, &p->launches));
+      }
       a.w_rec[d] = w + q.w_rec;
       a.b_rec[d] = w + q.b_rec;
       a.gates[d] = gates;
       a.cell[d] = rs ? rs + p->r_cell[d][l] : nullptr;
     }
-    CK(rec_fp32_forward(a, stream));
+    {
+      Timed tm(p, 0, stream);
+      CK(rec_fp32_forward(a, stream));
+    }
     p->launches++;
   }
   return B200RNN_STATUS_SUCCESS;
@@ -293,7 +333,10 @@ b200rnnStatus_t b200rnnBackwardData(b200rnnPlan_t p, int T, const float *y, cons
       a.gates[d] = rs + p->r_gates[d][l];
       a.cell[d] = rs + p->r_cell[d][l];
     }
-    CK(rec_fp32_backward(a, stream));
+    {
+      Timed tm(p, 1, stream);
+      CK(rec_fp32_backward(a, stream));
+    }
     p->launches++;
     if (dxl) {
       for (int d = 0; d < p->dirs; d++) {
@@ -304,6 +347,7 @@ b200rnnStatus_t b200rnnBackwardData(b200rnnPlan_t p, int T, const float *y, cons
         g.B = w + q.w_in; g.sbk = din; g.sbn = 1;
         g.C = dxl; g.ldc = din;
         g.splits = 1;
+        Timed tm(p, 2, stream);
         CK(gemm_fp32(g, stream, &p->launches));
       }
     }
@@ -335,7 +379,10 @@ b200rnnStatus_t b200rnnBackwardWeights(b200rnnPlan_t p, int T, const float *x, c
       g.B = in; g.sbk = din; g.sbn = 1;
       g.C = dw + q.w_in; g.ldc = din;
       g.splits = kSplitK; g.partial = ws + p->w_splitk;
-      CK(gemm_fp32(g, stream, &p->launches));
+      {
+        Timed tm(p, 2, stream);
+        CK(gemm_fp32(g, stream, &p->launches));
+      }
       // dR += dGrec^T . h_prev    h_prev(t) = y(t -+ 1): a row shift of B
       if (T > 1) {
         const int K = (T - 1) * B;
@@ -347,22 +394,26 @@ b200rnnStatus_t b200rnnBackwardWeights(b200rnnPlan_t p, int T, const float *x, c
         r.M = p->mode == 3 ? 2 * H : GH;
         r.A = dg + sh_g * GH; r.sam = 1; r.sak = GH;
         r.C = dw + q.w_rec;
-        CK(gemm_fp32(r, stream, &p->launches));
+        {
+          Timed tm(p, 2, stream);
+          CK(gemm_fp32(r, stream, &p->launches));
+        }
         if (p->mode == 3) {  // n-gate: recurrent-side gradient lives in the cell buffer
           r.M = H;
           r.A = dq + sh_g * H; r.sam = 1; r.sak = H;
           r.C = dw + q.w_rec + (size_t)2 * H * H;
+          Timed tm(p, 2, stream);
           CK(gemm_fp32(r, stream, &p->launches));
         }
       }
       // biases
       float *part = ws + p->w_colsum;
-      CK(column_sums(dg, TB, GH, GH, dw + q.b_in, 1, part, p->colsum_floats, stream, &p->launches));
+      CK(column_sums(dg, TB, GH, GH, 1.f, dw + q.b_in, 1, part, p->colsum_floats, stream, &p->launches));
       if (p->mode == 3) {
-        CK(column_sums(dg, TB, 2 * H, GH, dw + q.b_rec, 1, part, p->colsum_floats, stream, &p->launches));
-        CK(column_sums(dq, TB, H, H, dw + q.b_rec + 2 * H, 1, part, p->colsum_floats, stream, &p->launches));
+        CK(column_sums(dg, TB, 2 * H, GH, 1.f, dw + q.b_rec, 1, part, p->colsum_floats, stream, &p->launches));
+        CK(column_sums(dq, TB, H, H, 1.f, dw + q.b_rec + 2 * H, 1, part, p->colsum_floats, stream, &p->launches));
       } else {
-        CK(column_sums(dg, TB, GH, GH, dw + q.b_rec, 1, part, p->colsum_floats, stream, &p->launches));
+        CK(column_sums(dg, TB, GH, GH, 1.f, dw + q.b_rec, 1, part, p->colsum_floats, stream, &p->launches));
       }
     }
   }
@@ -410,11 +461,11 @@ b200rnnStatus_t b200rnnGemm(int transA, int transB, int M, int N, int K, float a
   return to_status(gemm_fp32(g, (cudaStream_t)stream, nullptr));
 }
 
-b200rnnStatus_t b200rnnColumnSums(const float *a, int rows, int cols, int lda, float *out,
-                                  int accumulate, void *workspace, size_t workspace_bytes,
-                                  b200rnnStream_t stream) {
+b200rnnStatus_t b200rnnColumnSums(const float *a, int rows, int cols, int lda, float alpha,
+                                  float *out, int accumulate, void *workspace,
+                                  size_t workspace_bytes, b200rnnStream_t stream) {
   if (!a || !out || !workspace) return B200RNN_STATUS_INVALID_VALUE;
-  cudaError_t e = column_sums(a, rows, cols, lda, out, accumulate, static_cast<float *>(workspace),
+  cudaError_t e = column_sums(a, rows, cols, lda, alpha, out, accumulate, static_cast<float *>(workspace),
                               workspace_bytes / sizeof(float), (cudaStream_t)stream, nullptr);
   return e == cudaErrorInvalidValue ? B200RNN_STATUS_INVALID_VALUE : to_status(e);
 }
@@ -425,6 +476,28 @@ double b200rnnForwardFlops(b200rnnPlan_t p, int T) {
   for (int l = 0; l < p->layers; l++)
     per += (double)p->dirs * 2.0 * p->GH * ((double)din_of(p, l) + p->H);
   return per * T * p->B;
+}
+
+b200rnnStatus_t b200rnnSetProfiling(b200rnnPlan_t p, int enable) {
+  if (!p) return B200RNN_STATUS_INVALID_VALUE;
+  p->profiling = enable != 0;
+  return B200RNN_STATUS_SUCCESS;
+}
+
+b200rnnStatus_t b200rnnGetProfile(b200rnnPlan_t p, int category, float *total_ms, int *launches) {
+  if (!p || category < 0 || category > 2 || !total_ms || !launches) return B200RNN_STATUS_INVALID_VALUE;
+  float tot = 0.f;
+  for (size_t i = 0; i < p->ev_used[category]; i++) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(p->ev[category][i].second) != cudaSuccess ||
+        cudaEventElapsedTime(&ms, p->ev[category][i].first, p->ev[category][i].second) != cudaSuccess)
+      return B200RNN_STATUS_EXECUTION_FAILED;
+    tot += ms;
+  }
+  *total_ms = tot;
+  *launches = (int)p->ev_used[category];
+  p->ev_used[category] = 0;
+  return B200RNN_STATUS_SUCCESS;
 }
 
 int b200rnnLastLaunchCount(b200rnnPlan_t p) { return p ? p->launches : 0; }

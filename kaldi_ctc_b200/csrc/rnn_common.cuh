@@ -42,7 +42,7 @@ struct GemmArgs {
   float *partial;
 };
 cudaError_t gemm_fp32(const GemmArgs &g, cudaStream_t stream, int *launches);
-cudaError_t column_sums(const float *a, int rows, int cols, int lda, float *out, int accumulate,
+cudaError_t column_sums(const float *a, int rows, int cols, int lda, float alpha, float *out, int accumulate,
                         float *partial, size_t partial_floats, cudaStream_t stream, int *launches);
 size_t column_sums_partial_floats(int rows, int cols);
 

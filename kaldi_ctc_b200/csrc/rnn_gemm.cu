@@ -142,12 +142,12 @@ __global__ void colsum_partial_kernel(const float *a, int rows, int cols, int ld
     partial[(size_t)blockIdx.y * cols + c] = t;
   }
 }
-__global__ void colsum_final_kernel(const float *partial, int cols, float *out, int accumulate) {
+__global__ void colsum_final_kernel(const float *partial, int cols, float alpha, float *out, int accumulate) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   float s = 0.f;
   for (int z = 0; z < kColSplit; z++) s += partial[(size_t)z * cols + c];
-  out[c] = accumulate ? out[c] + s : s;
+  out[c] = accumulate ? fmaf(alpha, s, out[c]) : alpha * s;
 }
 
 }  // namespace
@@ -175,12 +175,12 @@ cudaError_t gemm_fp32(const GemmArgs &g0, cudaStream_t stream, int *launches) {
 
 size_t column_sums_partial_floats(int rows, int cols) { return (size_t)kColSplit * cols; }
 
-cudaError_t column_sums(const float *a, int rows, int cols, int lda, float *out, int accumulate,
+cudaError_t column_sums(const float *a, int rows, int cols, int lda, float alpha, float *out, int accumulate,
                         float *partial, size_t partial_floats, cudaStream_t stream, int *launches) {
   if (partial_floats < (size_t)kColSplit * cols) return cudaErrorInvalidValue;
   dim3 grid((cols + 31) / 32, kColSplit);
   colsum_partial_kernel<<<grid, 256, 0, stream>>>(a, rows, cols, lda, partial);
-  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(partial, cols, out, accumulate);
+  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(partial, cols, alpha, out, accumulate);
   if (launches) (*launches) += 2;
   return cudaGetLastError();
 }

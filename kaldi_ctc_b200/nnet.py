@@ -1,0 +1,226 @@
+"""Host-side mirror of the training step of nnet2-ctc-train-simple:
+kaldi::ctc::NnetCtcUpdater::ComputeForMinibatch (src/ctc/ctc-nnet-update.cc:94-127)
+over the 'cudnn_google' topology that steps/ctc/nnet2/make_configs.py emits:
+
+    [CuDNNRecurrentComponent -> ClipGradientComponent] x N -> AffineComponent -> CTC
+
+Same order of operations as the reference: FormatInput (H2D of the time-major
+slab, :107-111), SetMiniBatch (:117), Propagate (:136-169), ComputeObjfAndDeriv
+(:171-259, the warp-ctc call), Backprop with the derivative negated (:320-348),
+each updatable component applying w += lr * grad as it goes.  Every FLOP runs in
+libb200ctc.so / libb200rnn.so; torch only owns device memory and streams.
+"""
+import numpy as np
+
+from . import _lib, ctc, rnn
+
+
+class AffineComponent:
+    """nnet2 AffineComponent (src/nnet2/nnet-component.cc:1184-1226): y = x W^T + b."""
+
+    def __init__(self, linear_params, bias_params, learning_rate, device="cuda:0", math=rnn.MATH_FP32):
+        self.torch = _lib.require_cuda()
+        t = self.torch
+        self.device = t.device(device)
+        self.linear_params_ = t.as_tensor(np.asarray(linear_params, np.float32)).to(self.device).clone()
+        self.bias_params_ = t.as_tensor(np.asarray(bias_params, np.float32)).to(self.device).clone()
+        self.learning_rate_ = learning_rate
+        self.math = math
+        self.ws = t.empty(32 << 20, dtype=t.uint8, device=self.device)
+
+    def InputDim(self):
+        return self.linear_params_.shape[1]
+
+    def OutputDim(self):
+        return self.linear_params_.shape[0]
+
+    def Propagate(self, inp, out=None):
+        t = self.torch
+        rows, K, N = inp.shape[0], self.InputDim(), self.OutputDim()
+        if out is None:
+            out = t.empty(rows, N, device=self.device)
+        rnn.gemm(t, 0, 1, rows, N, K, 1.0, inp, K, self.linear_params_, K, 0.0, out, N,
+                 bias=self.bias_params_, math=self.math)
+        return out
+
+    def Backprop(self, in_value, out_deriv, to_update=None, in_deriv=None, grad_out=None):
+        t = self.torch
+        rows, K, N = in_value.shape[0], self.InputDim(), self.OutputDim()
+        if in_deriv is None:
+            in_deriv = t.empty(rows, K, device=self.device)
+        rnn.gemm(t, 0, 0, rows, K, N, 1.0, out_deriv, N, self.linear_params_, K, 0.0, in_deriv, K, math=self.math)
+        if to_update is not None and grad_out is None:
+            # UpdateSimple: bias += lr * colsum, W += lr * dY^T X
+            rnn.column_sums_scaled(t, out_deriv, to_update.bias_params_, to_update.learning_rate_, self.ws)
+            rnn.gemm(t, 1, 0, N, K, rows, to_update.learning_rate_, out_deriv, N, in_value, K, 1.0,
+                     to_update.linear_params_, K, math=self.math, workspace=self.ws)
+        elif grad_out is not None:  # data-parallel: raw gradients, applied after the all-reduce
+            gW, gb = grad_out
+            rnn.column_sums(t, out_deriv, gb, False, self.ws)
+            rnn.gemm(t, 1, 0, N, K, rows, 1.0, out_deriv, N, in_value, K, 0.0, gW, K, math=self.math,
+                     workspace=self.ws)
+        return in_deriv
+
+    def Update(self, gW, gb):
+        t = self.torch
+        rnn.clip_and_update(t, self.linear_params_, gW, self.learning_rate_, 0.0)
+        rnn.clip_and_update(t, self.bias_params_, gb, self.learning_rate_, 0.0)
+
+
+class ClipGradientComponent:
+    """nnet2 ClipGradientComponent, norm-based (nnet-cudnn-component.cc:912-957):
+    identity forward; backward scales each derivative row to L2 norm <= threshold.
+    (The optional stochastic self-repair, :980-1055, is off at the recipe's
+    self_repair_scale=1e-5 start-up state: count_ == 0.)"""
+
+    def __init__(self, dim, clipping_threshold=30.0):
+        self.dim_, self.clipping_threshold_ = dim, clipping_threshold
+        self.torch = _lib.require_cuda()
+
+    def Propagate(self, inp):
+        return inp  # out->CopyFromMat(in): the copy is elided, the values are identical
+
+    def Backprop(self, out_deriv):
+        if self.clipping_threshold_ > 0:
+            rnn.clip_row_norm(self.torch, out_deriv, self.clipping_threshold_)
+        return out_deriv
+
+
+class _Grab:
+    """to_update stand-in that leaves the raw gradient in the component's buffer."""
+
+    def Update(self, grad, clip):
+        pass
+
+
+class NnetCtcUpdater:
+    """Mirror of kaldi::ctc::NnetCtcUpdater for the BLSTM/BiGRU + CTC topology."""
+
+    def __init__(self, spec, blobs, affine_w, affine_b, minibatch, max_frames, device="cuda:0",
+                 math=rnn.MATH_FP32, world=1):
+        self.torch = t = _lib.require_cuda()
+        self.device = t.device(device)
+        self.spec, self.B, self.math, self.world = spec, minibatch, math, world
+        dirs = 2 if spec.bidir else 1
+        self.rnns, self.clips = [], []
+        for l, blob in enumerate(blobs):
+            c = rnn.CuDNNRecurrentComponent(device, math=math)
+            c.InitFromString(
+                "learning-rate=%g num-layers=1 input-dim=%d output-dim=%d rnn-mode=%d bidirectional=%s "
+                "max-seq-length=%d clip-gradient=%g mini-batch=%d" %
+                (spec.learning_rate, spec.D if l == 0 else spec.H * dirs, spec.H, spec.mode,
+                 "true" if spec.bidir else "false", max_frames, spec.clip_gradient, minibatch))
+            c.SetParams(blob)
+            self.rnns.append(c)
+            self.clips.append(ClipGradientComponent(spec.H * dirs, spec.clipping_threshold))
+        self.affine = AffineComponent(affine_w, affine_b, spec.learning_rate, device, math)
+        self.ctc = ctc.CtcLoss(device)
+        self.max_frames = max_frames
+        rows = max_frames * minibatch
+        # forward_data_ of the reference: one buffer per component boundary, reused every minibatch
+        self.x_dev = t.empty(rows, spec.D, device=self.device)
+        self.acts = [t.empty(rows, spec.H * dirs, device=self.device) for _ in blobs]
+        self.logits = t.empty(rows, spec.A, device=self.device)
+        self.deriv = t.empty(rows, spec.A, device=self.device)
+        self.dact = [t.empty(rows, spec.H * dirs, device=self.device) for _ in range(2)]
+        self.costs_dev = t.zeros(minibatch, device=self.device)
+        self.costs_host = t.zeros(minibatch, dtype=t.float32).pin_memory()
+        if world > 1:  # data-parallel gradient buffers of the affine layer
+            self.gW = t.zeros_like(self.affine.linear_params_)
+            self.gb = t.zeros_like(self.affine.bias_params_)
+
+    def SetMiniBatch(self, B):
+        for c in self.rnns:
+            c.InitMiniBatch(B)
+
+    def FormatInput(self, feats_host, T):
+        """feats_host: pinned [T*B, D] float32 (FormatNnetInput's output) -> device."""
+        rows = T * self.B
+        self.x_dev[:rows].copy_(feats_host[:rows], non_blocking=True)
+
+    def Propagate(self, T):
+        rows = T * self.B
+        h = self.x_dev[:rows]
+        for c, clip, out in zip(self.rnns, self.clips, self.acts):
+            h = clip.Propagate(c.Propagate(h, out[:rows]))
+        return self.affine.Propagate(h, self.logits[:rows])
+
+    def ComputeObjfAndDeriv(self, T, flat_labels, label_lengths, input_lengths, sync=True):
+        rows = T * self.B
+        act = self.logits[:rows].view(T, self.B, self.spec.A)
+        grad = self.deriv[:rows].view(T, self.B, self.spec.A)
+        # grad_scale=-1 fuses deriv->Scale(-1) of NnetCtcUpdater::Backprop (:323)
+        self.ctc.compute_extended(act, flat_labels, label_lengths, input_lengths, blank=0, gradients=grad,
+                                  grad_scale=-1.0, costs_dev=self.costs_dev, no_sync=True)
+        self.costs_host.copy_(self.costs_dev, non_blocking=True)
+        if sync:
+            self.torch.cuda.current_stream(self.device).synchronize()
+            return float(self.costs_host.sum())
+        return None
+
+    def Backprop(self, T, update=True):
+        """world == 1: the reference's flow, every component updates itself as the
+        derivative passes through it.  world > 1 (utterance-sharded data parallel,
+        SURVEY 8(e)): each component's raw gradient is summed over ranks with an
+        asynchronous NCCL all-reduce issued as soon as it exists (top layer first, so
+        it overlaps the lower layers' backward), then clipped and applied on every rank."""
+        rows = T * self.B
+        n = len(self.rnns)
+        top_in = self.acts[-1][:rows]
+        dp = update and self.world > 1
+        pending = []
+        if dp:
+            import torch.distributed as dist
+            d = self.affine.Backprop(top_in, self.deriv[:rows], None, in_deriv=self.dact[0][:rows],
+                                     grad_out=(self.gW, self.gb))
+            pending.append((dist.all_reduce(self.gW, async_op=True), None))
+            pending.append((dist.all_reduce(self.gb, async_op=True), "affine"))
+        else:
+            d = self.affine.Backprop(top_in, self.deriv[:rows], self.affine if update else None,
+                                     in_deriv=self.dact[0][:rows])
+        for l in range(n - 1, -1, -1):
+            d = self.clips[l].Backprop(d)
+            inp = self.x_dev[:rows] if l == 0 else self.acts[l - 1][:rows]
+            comp = self.rnns[l]
+            if dp:
+                grab = _Grab()
+                d = comp.Backprop(inp, self.acts[l][:rows], d, to_update=grab, want_in_deriv=(l > 0))
+                pending.append((dist.all_reduce(comp.filter_params_grad_, async_op=True), comp))
+            else:
+                d = comp.Backprop(inp, self.acts[l][:rows], d, to_update=comp if update else None,
+                                  want_in_deriv=(l > 0))
+        for work, who in pending:
+            work.wait()
+            if who == "affine":
+                self.affine.Update(self.gW, self.gb)
+            elif who is not None:
+                who.Update(who.filter_params_grad_, who.clip_gradient_)
+        return d
+
+    def ComputeForMinibatch(self, feats_host, T, flat_labels, label_lengths, input_lengths, update=True,
+                            host_sync=True):
+        """One training step; returns tot_objf = sum of the per-utterance NLLs (:256).
+        feats_host=None keeps the slab already resident in x_dev; host_sync=False leaves the
+        step asynchronous (read the objective later with last_objf())."""
+        if feats_host is not None:
+            self.FormatInput(feats_host, T)
+        self.Propagate(T)
+        self.ComputeObjfAndDeriv(T, flat_labels, label_lengths, input_lengths, sync=False)
+        self.Backprop(T, update)
+        if not host_sync:
+            return None
+        return self.last_objf()
+
+    def last_objf(self):
+        self.torch.cuda.current_stream(self.device).synchronize()
+        return float(self.costs_host.sum())
+
+    def launches_per_step(self):
+        """Kernels of OUR libraries launched by one ComputeForMinibatch (fp32 mode
+        bookkeeping comes from the plans; + affine 3 GEMMs (+split-K reduce) + colsum 2 + CTC 3
+        + clip per layer + update per layer)."""
+        n = 0
+        for c in self.rnns:
+            n += c.launch_counts.get("fwd", 0) + c.launch_counts.get("bwd_data", 0) + \
+                c.launch_counts.get("bwd_weights", 0) + 1 + 1  # + ClipAndUpdate + ClipRowNorm
+        return n + 3 + 4 + 2

@@ -42,7 +42,9 @@ def lib():
         L.b200rnnClipAndUpdate.argtypes = [vp, vp, sz, f, f, vp]
         L.b200rnnClipRowNorm.argtypes = [vp, i, i, f, vp]
         L.b200rnnGemm.argtypes = [i, i, i, i, i, f, vp, i, vp, i, f, vp, i, vp, i, vp, sz, vp]
-        L.b200rnnColumnSums.argtypes = [vp, i, i, i, vp, i, vp, sz, vp]
+        L.b200rnnColumnSums.argtypes = [vp, i, i, i, f, vp, i, vp, sz, vp]
+        L.b200rnnSetProfiling.argtypes = [vp, i]
+        L.b200rnnGetProfile.argtypes = [vp, i, ctypes.POINTER(f), ctypes.POINTER(i)]
         L.b200rnnForwardFlops.restype = ctypes.c_double
         L.b200rnnForwardFlops.argtypes = [vp, i]
         L.b200rnnLastLaunchCount.argtypes = [vp]
@@ -104,6 +106,14 @@ class Plan:
     def last_launches(self):
         return lib().b200rnnLastLaunchCount(self.h)
 
+    def set_profiling(self, enable):
+        _check(lib().b200rnnSetProfiling(self.h, int(enable)), "b200rnnSetProfiling")
+
+    def get_profile(self, category):
+        ms, n = ctypes.c_float(), ctypes.c_int()
+        _check(lib().b200rnnGetProfile(self.h, category, ctypes.byref(ms), ctypes.byref(n)), "b200rnnGetProfile")
+        return ms.value, n.value
+
 
 def _stream(torch, device):
     return torch.cuda.current_stream(device).cuda_stream
@@ -126,6 +136,7 @@ class CuDNNRecurrentComponent:
         self.param_stddev_, self.bias_stddev_, self.clip_gradient_ = 0.02, 0.2, 5.0
         self.filter_params_ = None
         self.plan = None
+        self.launch_counts = {}
 
     def Type(self):
         return "CuDNNRecurrentComponent"
@@ -196,6 +207,7 @@ class CuDNNRecurrentComponent:
             _check(lib().b200rnnForward(self.plan.h, T, inp.data_ptr(), self.filter_params_.data_ptr(),
                                         out.data_ptr(), self.work_space_.data_ptr(), reserve,
                                         _stream(torch, self.device)), "b200rnnForward")
+        self.launch_counts["fwd"] = self.plan.last_launches()
         return out
 
     def Backprop(self, in_value, out_value, out_deriv, to_update=None, want_in_deriv=True):
@@ -210,12 +222,14 @@ class CuDNNRecurrentComponent:
                                              in_deriv.data_ptr() if want_in_deriv else None,
                                              self.work_space_.data_ptr(), self.reserve_space_.data_ptr(), s),
                    "b200rnnBackwardData")
+            self.launch_counts["bwd_data"] = self.plan.last_launches()
             if to_update is not None:
                 self.filter_params_grad_.zero_()
                 _check(lib().b200rnnBackwardWeights(self.plan.h, T, in_value.data_ptr(), out_value.data_ptr(),
                                                     self.filter_params_grad_.data_ptr(),
                                                     self.work_space_.data_ptr(), self.reserve_space_.data_ptr(), s),
                        "b200rnnBackwardWeights")
+                self.launch_counts["bwd_weights"] = self.plan.last_launches()
                 to_update.Update(self.filter_params_grad_, self.clip_gradient_)
         return in_deriv
 
@@ -259,11 +273,21 @@ def gemm(torch, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bi
                              _stream(torch, C.device)), "b200rnnGemm")
 
 
-def column_sums(torch, a, out, accumulate, workspace):
+def column_sums(torch, a, out, accumulate, workspace, alpha=1.0):
     rows, cols = a.shape
-    _check(lib().b200rnnColumnSums(a.data_ptr(), rows, cols, a.stride(0), out.data_ptr(), int(accumulate),
+    _check(lib().b200rnnColumnSums(a.data_ptr(), rows, cols, a.stride(0), alpha, out.data_ptr(), int(accumulate),
                                    workspace.data_ptr(), workspace.numel() * workspace.element_size(),
                                    _stream(torch, a.device)), "b200rnnColumnSums")
+
+
+def column_sums_scaled(torch, a, out, alpha, workspace):
+    """out += alpha * colsum(a)"""
+    column_sums(torch, a, out, True, workspace, alpha=alpha)
+
+
+def clip_and_update(torch, w, dw, lr, clip):
+    _check(lib().b200rnnClipAndUpdate(w.data_ptr(), dw.data_ptr(), w.numel(), lr, clip,
+                                      _stream(torch, w.device)), "b200rnnClipAndUpdate")
 
 
 def clip_row_norm(torch, d, threshold):
