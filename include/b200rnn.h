@@ -126,6 +126,10 @@ b200rnnStatus_t b200rnnGemm(int transA, int transB, int M, int N, int K, float a
                             int ldc, const float *bias, b200rnnMath_t math, void *workspace,
                             size_t workspace_bytes, b200rnnStream_t stream);
 
+/* 1 if the most recent GEMM issued by this library ran on tcgen05 (MATH_TENSOR with
+ * TMA-compatible operands), 0 if it took the fp32 FMA path. */
+int b200rnnLastGemmUsedTensorCores(void);
+
 /* Column sums: out[c] = (accumulate ? out[c] : 0) + alpha * sum_r a[r, c]
  * (AffineComponent bias update: bias += lr * colsum(deriv)).  Deterministic. */
 b200rnnStatus_t b200rnnColumnSums(const float *a, int rows, int cols, int lda, float alpha,

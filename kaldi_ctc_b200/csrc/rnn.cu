@@ -290,7 +290,7 @@ b200rnnStatus_t b200rnnForward(b200rnnPlan_t p, int T, const float *x, const flo
       g.splits = 1; g.partial = nullptr;
       {
         Timed tm(p, 2, stream);
-        CK(gemm_fp32(g, stream, &p->launches));
+        CK(gemm_any(p->math, g, stream, &p->launches));
       }
       a.w_rec[d] = w + q.w_rec;
       a.b_rec[d] = w + q.b_rec;
@@ -348,7 +348,7 @@ b200rnnStatus_t b200rnnBackwardData(b200rnnPlan_t p, int T, const float *y, cons
         g.C = dxl; g.ldc = din;
         g.splits = 1;
         Timed tm(p, 2, stream);
-        CK(gemm_fp32(g, stream, &p->launches));
+        CK(gemm_any(p->math, g, stream, &p->launches));
       }
     }
   }
@@ -381,7 +381,7 @@ b200rnnStatus_t b200rnnBackwardWeights(b200rnnPlan_t p, int T, const float *x, c
       g.splits = kSplitK; g.partial = ws + p->w_splitk;
       {
         Timed tm(p, 2, stream);
-        CK(gemm_fp32(g, stream, &p->launches));
+        CK(gemm_any(p->math, g, stream, &p->launches));
       }
       // dR += dGrec^T . h_prev    h_prev(t) = y(t -+ 1): a row shift of B
       if (T > 1) {
@@ -396,14 +396,14 @@ b200rnnStatus_t b200rnnBackwardWeights(b200rnnPlan_t p, int T, const float *x, c
         r.C = dw + q.w_rec;
         {
           Timed tm(p, 2, stream);
-          CK(gemm_fp32(r, stream, &p->launches));
+          CK(gemm_any(p->math, r, stream, &p->launches));
         }
         if (p->mode == 3) {  // n-gate: recurrent-side gradient lives in the cell buffer
           r.M = H;
           r.A = dq + sh_g * H; r.sam = 1; r.sak = H;
           r.C = dw + q.w_rec + (size_t)2 * H * H;
           Timed tm(p, 2, stream);
-          CK(gemm_fp32(r, stream, &p->launches));
+          CK(gemm_any(p->math, r, stream, &p->launches));
         }
       }
       // biases
@@ -442,7 +442,6 @@ b200rnnStatus_t b200rnnGemm(int transA, int transB, int M, int N, int K, float a
                             int ldc, const float *bias, b200rnnMath_t math, void *workspace,
                             size_t workspace_bytes, b200rnnStream_t stream) {
   if (!A || !B || !C || M < 0 || N < 0 || K < 0) return B200RNN_STATUS_INVALID_VALUE;
-  (void)math;
   GemmArgs g = {};
   g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta;
   g.A = A; g.sam = transA ? 1 : lda; g.sak = transA ? lda : 1;
@@ -458,7 +457,7 @@ b200rnnStatus_t b200rnnGemm(int transA, int transB, int M, int N, int K, float a
       g.partial = static_cast<float *>(workspace);
     }
   }
-  return to_status(gemm_fp32(g, (cudaStream_t)stream, nullptr));
+  return to_status(gemm_any((int)math, g, (cudaStream_t)stream, nullptr));
 }
 
 b200rnnStatus_t b200rnnColumnSums(const float *a, int rows, int cols, int lda, float alpha,
@@ -499,6 +498,8 @@ b200rnnStatus_t b200rnnGetProfile(b200rnnPlan_t p, int category, float *total_ms
   p->ev_used[category] = 0;
   return B200RNN_STATUS_SUCCESS;
 }
+
+int b200rnnLastGemmUsedTensorCores(void) { return g_last_gemm_tc; }
 
 int b200rnnLastLaunchCount(b200rnnPlan_t p) { return p ? p->launches : 0; }
 

@@ -42,6 +42,14 @@ struct GemmArgs {
   float *partial;
 };
 cudaError_t gemm_fp32(const GemmArgs &g, cudaStream_t stream, int *launches);
+// C = beta*C + bias + sum_z partial[z]  (fixed summation order)
+cudaError_t splitk_reduce(const GemmArgs &g, cudaStream_t stream);
+// tcgen05 kind::tf32 GEMM fed by TMA (rnn_gemm_tc.cu); cudaErrorNotSupported when the
+// operands break TMA's alignment rules (16-byte base, row pitch % 4 floats)
+cudaError_t gemm_tc(const GemmArgs &g, cudaStream_t stream, int *launches);
+// math: 0 = fp32 FMA, 1 = tensor cores with fp32 fallback for unaligned operands
+extern int g_last_gemm_tc;  // 1 if the last gemm_any ran on tcgen05
+cudaError_t gemm_any(int math, const GemmArgs &g, cudaStream_t stream, int *launches);
 cudaError_t column_sums(const float *a, int rows, int cols, int lda, float alpha, float *out, int accumulate,
                         float *partial, size_t partial_floats, cudaStream_t stream, int *launches);
 size_t column_sums_partial_floats(int rows, int cols);

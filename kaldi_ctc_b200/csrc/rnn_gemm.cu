@@ -166,11 +166,32 @@ cudaError_t gemm_fp32(const GemmArgs &g0, cudaStream_t stream, int *launches) {
   else sgemm_kernel<false, false><<<grid, 256, 0, stream>>>(g, kps);
   if (launches) (*launches)++;
   if (g.splits > 1) {
-    const size_t total = (size_t)g.M * g.N;
-    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256), 256, 0, stream>>>(g);
     if (launches) (*launches)++;
+    return splitk_reduce(g, stream);
   }
   return cudaGetLastError();
+}
+
+cudaError_t splitk_reduce(const GemmArgs &g, cudaStream_t stream) {
+  const size_t total = (size_t)g.M * g.N;
+  const size_t blocks = (total + 255) / 256;
+  splitk_reduce_kernel<<<(unsigned)(blocks > 1184 ? 1184 : blocks), 256, 0, stream>>>(g);
+  return cudaGetLastError();
+}
+
+int g_last_gemm_tc = 0;
+
+cudaError_t gemm_any(int math, const GemmArgs &g, cudaStream_t stream, int *launches) {
+  g_last_gemm_tc = 0;
+  if (math == 1) {
+    cudaError_t e = gemm_tc(g, stream, launches);
+    if (e != cudaErrorNotSupported) {
+      g_last_gemm_tc = 1;
+      return e;
+    }
+    cudaGetLastError();
+  }
+  return gemm_fp32(g, stream, launches);
 }
 
 size_t column_sums_partial_floats(int rows, int cols) { return (size_t)kColSplit * cols; }

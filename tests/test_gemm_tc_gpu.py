@@ -1,0 +1,57 @@
+"""The TMA-fed tcgen05 (kind::tf32) GEMM of libb200rnn.so against numpy fp64, for
+every operand-major combination the recurrent layers use.  TF32 keeps 10 mantissa
+bits of each operand (fp32 accumulation): tolerance 2e-3 of sum|a||b|."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # tA tB  M     N    K      (what it is in the model)
+    (0, 1, 512, 1280, 40),     # layer-1 input projection   x . Wi^T
+    (0, 1, 777, 1280, 640),    # layers 2-5 projection, ragged M
+    (0, 0, 640, 640, 1280),    # dx = dG . Wi
+    (1, 0, 1280, 640, 4096),   # dWi = dG^T . x   (split-K)
+    (1, 0, 1280, 320, 3000),   # dR  = dG^T . h_prev
+    (0, 1, 1000, 48, 640),     # affine forward, N = 48
+    (1, 0, 48, 640, 5000),     # affine weight gradient
+    (1, 1, 200, 136, 96),      # remaining combination
+    (0, 1, 130, 260, 33 * 4),  # K not a multiple of the 32-wide k-block
+]
+
+
+@pytest.mark.parametrize("tA,tB,M,N,K", CASES)
+def test_tc_gemm(tA, tB, M, N, K):
+    import torch
+    from kaldi_ctc_b200 import rnn
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = rng.standard_normal((K, M) if tA else (M, K)).astype(np.float32)
+    Bm = rng.standard_normal((N, K) if tB else (K, N)).astype(np.float32)
+    C0 = rng.standard_normal((M, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    opA, opB = (A.T if tA else A).astype(np.float64), (Bm.T if tB else Bm).astype(np.float64)
+    want = 0.5 * (opA @ opB) + 2.0 * C0 + bias
+    bound = 0.5 * (np.abs(opA) @ np.abs(opB))
+    At, Bt, Ct, bt = (torch.from_numpy(v).cuda() for v in (A, Bm, C0.copy(), bias))
+    ws = torch.empty(128 << 20, dtype=torch.uint8, device="cuda")
+    rnn.gemm(torch, tA, tB, M, N, K, 0.5, At, A.shape[1], Bt, Bm.shape[1], 2.0, Ct, N, bias=bt,
+             math=rnn.MATH_TENSOR, workspace=ws)
+    torch.cuda.synchronize()
+    assert rnn.lib().b200rnnLastGemmUsedTensorCores() == 1, "fell back to the fp32 path"
+    err = np.abs(Ct.cpu().numpy() - want)
+    assert (err <= 2e-3 * bound + 1e-4).all(), "max err %g (bound %g)" % (err.max(), (2e-3 * bound).max())
+    # and it is genuinely TF32 (not fp32): some rounding must be visible at K >= 640
+    if K >= 640:
+        assert err.max() > 1e-6
+
+
+def test_unaligned_operands_fall_back_to_fp32():
+    import torch
+    from kaldi_ctc_b200 import rnn
+    A = torch.randn(50, 37, device="cuda")      # row pitch 37 floats: not 16-byte aligned rows
+    Bm = torch.randn(20, 37, device="cuda")
+    C = torch.zeros(50, 20, device="cuda")
+    rnn.gemm(torch, 0, 1, 50, 20, 37, 1.0, A, 37, Bm, 37, 0.0, C, 20, math=rnn.MATH_TENSOR)
+    torch.cuda.synchronize()
+    assert rnn.lib().b200rnnLastGemmUsedTensorCores() == 0
+    np.testing.assert_allclose(C.cpu().numpy(), (A @ Bm.T).cpu().numpy(), atol=1e-4)
