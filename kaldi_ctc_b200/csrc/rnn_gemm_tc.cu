@@ -112,12 +112,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t a = smem_u32(sA + s * kTileBytes), b = smem_u32(sB + s * kTileBytes);
 #pragma unroll
         for (int k = 0; k < TBK / 8; k++) {
-          // K-major: 8-row groups are 1024 B apart; a K step of 8 tf32 = +32 B inside the swizzle row
-          // MN-major: 32-wide MN blocks are TBK*128 B apart (LBO), 8 K-rows = 1024 B (SBO and K step)
-          const uint64_t ad = A_KMAJOR ? smem_desc_sw128(a + k * 32, 0, 1024)
-                                       : smem_desc_sw128(a + k * 1024, TBK * 128, 1024);
-          const uint64_t bd = B_KMAJOR ? smem_desc_sw128(b + k * 32, 0, 1024)
-                                       : smem_desc_sw128(b + k * 1024, TBK * 128, 1024);
+          // K-major (SW128, 16 B chunks): 8-row groups are 1024 B apart (SBO); a K step of 8 tf32
+          //   is +32 B inside the 128 B swizzle row.
+          // MN-major tf32 must use the 32 B-chunk flavour of the 128 B swizzle: atoms of 4 K-rows
+          //   x 128 B (512 B apart = SBO), 32-wide MN blocks TBK*128 B apart (LBO); a K step of
+          //   8 rows is +1024 B.
+          const uint64_t ad = A_KMAJOR ? smem_desc(a + k * 32, 0, 1024, kLayoutSw128)
+                                       : smem_desc(a + k * 1024, TBK * 128, 512, kLayoutSw128Base32);
+          const uint64_t bd = B_KMAJOR ? smem_desc(b + k * 32, 0, 1024, kLayoutSw128)
+                                       : smem_desc(b + k * 1024, TBK * 128, 512, kLayoutSw128Base32);
           mma_tf32(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
         tc_commit(empty + s);                   // frees the smem stage when these MMAs retire
@@ -217,7 +220,7 @@ EncodeTiledFn encode_fn() {
 
 // fp32 matrix with `inner` contiguous elements per row, `outer` rows, row pitch ld
 bool make_map(CUtensorMap *map, const float *base, long long inner, long long outer, long long ld,
-              int box_inner, int box_outer) {
+              int box_inner, int box_outer, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 4) || inner <= 0 || outer <= 0) return false;
@@ -226,7 +229,7 @@ bool make_map(CUtensorMap *map, const float *base, long long inner, long long ou
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -255,8 +258,11 @@ cudaError_t gemm_tc(const GemmArgs &g, cudaStream_t stream, int *launches) {
   if (!ak && g.sam != 1) return cudaErrorNotSupported;
   if (!bk && g.sbn != 1) return cudaErrorNotSupported;
   CUtensorMap ta, tb;
-  bool ok = ak ? make_map(&ta, g.A, g.K, g.M, g.sam, TBK, TBM) : make_map(&ta, g.A, g.M, g.K, g.sak, 32, TBK);
-  ok = ok && (bk ? make_map(&tb, g.B, g.K, g.N, g.sbn, TBK, TBN) : make_map(&tb, g.B, g.N, g.K, g.sbk, 32, TBK));
+  const CUtensorMapSwizzle kmaj = CU_TENSOR_MAP_SWIZZLE_128B, mnmaj = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  bool ok = ak ? make_map(&ta, g.A, g.K, g.M, g.sam, TBK, TBM, kmaj)
+               : make_map(&ta, g.A, g.M, g.K, g.sak, 32, TBK, mnmaj);
+  ok = ok && (bk ? make_map(&tb, g.B, g.K, g.N, g.sbn, TBK, TBN, kmaj)
+                 : make_map(&tb, g.B, g.N, g.K, g.sbk, 32, TBK, mnmaj));
   if (!ok) return cudaErrorNotSupported;
 
   TcParams p;

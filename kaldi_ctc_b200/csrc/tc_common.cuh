@@ -116,9 +116,16 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // Shared-memory matrix descriptor, 128-byte swizzle:
 //   [0,14) start>>4   [16,30) leading byte offset>>4   [32,46) stride byte offset>>4
 //   [46,48) version = 1 (sm_100)   [61,64) layout type = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+constexpr uint32_t kLayoutSw128 = 2;         // 128-byte swizzle of 16-byte chunks  (Swizzle<3,4,3>)
+constexpr uint32_t kLayoutSw128Base32 = 1;   // 128-byte swizzle of 32-byte chunks  (Swizzle<2,5,2>):
+                                             // the only layout for MN-major 32-bit (tf32) operands
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return smem_desc(saddr, lbo_bytes, sbo_bytes, kLayoutSw128);
 }
 // Instruction descriptor for kind::tf32 / kind::f16 with fp32 accumulation:
 //   [4,6) D format (1 = f32)  [7,10) A format  [10,13) B format  (0 f16, 1 bf16, 2 tf32)
