@@ -20,7 +20,8 @@ struct b200rnnPlan_st {
   std::vector<PseudoLayer> pl;
   size_t param_count;
   // recurrent-kernel geometry, probed on first use (needs the device)
-  int NC, BC;
+  int NC, BC;        // fp32 kernels
+  int tcNC, tcBC;    // tcgen05 kernels (0 = not usable for this shape)
   bool geometry_ready;
   int launches;
   // reserve layout (floats), per layer
@@ -46,6 +47,11 @@ b200rnnStatus_t ensure_geometry(b200rnnPlan_st *p) {
   p->NC = rec_fp32_pick_cluster(p->mode, p->H);
   if (p->NC == 0) return B200RNN_STATUS_NOT_SUPPORTED;
   p->BC = 16;
+  p->tcNC = p->tcBC = 0;
+  if (p->math == 1 && rec_tc_supported(p->mode, p->H)) {
+    p->tcNC = p->H / 32;
+    p->tcBC = rec_tc_pick_chunk(p->H, p->B, p->dirs);
+  }
   p->geometry_ready = true;
   return B200RNN_STATUS_SUCCESS;
 }
@@ -299,7 +305,12 @@ b200rnnStatus_t b200rnnForward(b200rnnPlan_t p, int T, const float *x, const flo
     }
     {
       Timed tm(p, 0, stream);
-      CK(rec_fp32_forward(a, stream));
+      if (p->tcNC) {
+        a.NC = p->tcNC; a.U = 32; a.BC = p->tcBC;
+        CK(rec_tc_forward(a, stream));
+      } else {
+        CK(rec_fp32_forward(a, stream));
+      }
     }
     p->launches++;
   }

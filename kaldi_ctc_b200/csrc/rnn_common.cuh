@@ -78,4 +78,11 @@ cudaError_t rec_fp32_backward(const RecArgs &a, cudaStream_t stream);
 // largest usable cluster size for this geometry (0 if none), probing the device
 int rec_fp32_pick_cluster(int mode, int H);
 
+// ------------------------------------------------------------------------
+// recurrent kernels on tcgen05 (rnn_rec_tc.cu): BF16 operands, fp32 accumulate/state
+// ------------------------------------------------------------------------
+bool rec_tc_supported(int mode, int H);
+int rec_tc_pick_chunk(int H, int B, int dirs);
+cudaError_t rec_tc_forward(const RecArgs &a, cudaStream_t stream);  // a.NC = H/32, a.BC in {4,8,16}
+
 }  // namespace b200
