@@ -4,10 +4,10 @@ Stated tolerance of this mode (north_star: "within a stated bf16/TF32 tolerance"
 recurrent operands (R, h_{t-1}) are rounded to BF16 (8 mantissa bits), projections
 and weight gradients run in TF32 (10 bits), accumulation / cell state / outputs are
 fp32, gate non-linearities use tanh.approx (abs err 5e-4).  Against the fp64 oracle:
-    outputs y            max-abs <= 2e-2   (values in [-1, 1])
-    dx, dw               max-abs <= 3e-2 * max|ref|
+    outputs y            max-abs <= 5e-3   (values in [-1, 1]; measured 3e-4 .. 2e-3)
+    dx, dw               max-abs <= 1e-2 * max|ref|   (measured 6e-4 .. 1.6e-3)
 and against a numpy emulation that applies the SAME operand roundings (so only
-accumulation order and tanh.approx differ): y max-abs <= 3e-3.
+accumulation order and tanh.approx differ): y max-abs <= 1e-3 (measured <= 3.6e-4).
 """
 import numpy as np
 import pytest
@@ -101,6 +101,6 @@ def test_tensor_mode_within_stated_tolerance(mode, D, H, B, Tn):
     e_emul, e_y = np.abs(y - ye).max(), np.abs(y - yr).max()
     e_dx, e_dw = np.abs(dx - dxr).max() / np.abs(dxr).max(), np.abs(dw - dwr).max() / np.abs(dwr).max()
     print("tensor-mode errors: y vs emulation %.2e, y vs fp64 %.2e, dx rel %.2e, dw rel %.2e" % (e_emul, e_y, e_dx, e_dw))
-    assert e_emul < 3e-3
-    assert e_y < 2e-2
-    assert e_dx < 3e-2 and e_dw < 3e-2
+    assert e_emul < 1e-3
+    assert e_y < 5e-3
+    assert e_dx < 1e-2 and e_dw < 1e-2
