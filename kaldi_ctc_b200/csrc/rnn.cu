@@ -4,6 +4,7 @@
 // CuDNNRecurrentComponent gets from cuDNN 5 (src/nnet2/nnet-cudnn-component.cc
 // :100-315 descriptors, :534-555 forward, :576-599 backward).
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <new>
@@ -51,6 +52,10 @@ b200rnnStatus_t ensure_geometry(b200rnnPlan_st *p) {
   if (p->math == 1 && rec_tc_supported(p->mode, p->H)) {
     p->tcNC = p->H / 32;
     p->tcBC = rec_tc_pick_chunk(p->H, p->B, p->dirs);
+    if (const char *e = getenv("B200RNN_TC_BC")) {  // tuning override: 4, 8 or 16
+      const int v = atoi(e);
+      if (v == 4 || v == 8 || v == 16) p->tcBC = v;
+    }
   }
   p->geometry_ready = true;
   return B200RNN_STATUS_SUCCESS;
@@ -307,7 +312,20 @@ b200rnnStatus_t b200rnnForward(b200rnnPlan_t p, int T, const float *x, const flo
       Timed tm(p, 0, stream);
       if (p->tcNC) {
         a.NC = p->tcNC; a.U = 32; a.BC = p->tcBC;
+        static long long *dbg = nullptr;
+        const bool prof = getenv("B200RNN_TC_PROFILE") != nullptr;
+        if (prof && !dbg) cudaMalloc(&dbg, 64 * sizeof(long long));
+        a.dbg = prof ? dbg : nullptr;
         CK(rec_tc_forward(a, stream));
+        if (prof) {  // tuning aid: cycles per step of each phase (cluster 0, CTA 0)
+          long long h[16];
+          cudaStreamSynchronize(stream);
+          cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+          const double n = T;
+          fprintf(stderr, "[b200rnn fwd tc] cyc/step epilogue: wait_acc %.0f tmem_ld %.0f math %.0f pack+dsmem %.0f "
+                  "bar %.0f arrive %.0f gstore+prefetch %.0f | mma warp: wait_h %.0f fence %.0f issue %.0f\n",
+                  h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[8] / n, h[9] / n, h[10] / n);
+        }
       } else {
         CK(rec_fp32_forward(a, stream));
       }

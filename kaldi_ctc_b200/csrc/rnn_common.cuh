@@ -70,6 +70,7 @@ struct RecArgs {
   float *y;               // [T*B x H*dirs]
   const float *dy;        // bwd only
   int save;               // fwd: 1 = keep activations/cell for backward
+  long long *dbg;         // optional: per-phase cycle counters of cluster 0 / CTA 0 (tuning aid)
 };
 // smem bytes for a given geometry (0 = does not fit the fp32 persistent kernels)
 size_t rec_fp32_smem_bytes(int mode, int H, int NC, bool backward);

@@ -108,7 +108,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int it = kb - kb0, s = it % kStages;
       mbar_wait(full + s, (it / kStages) & 1);
       tc_fence_after();
-      if (lane == 0) {
+      {
+        // warp-uniform issue (descriptors stay in uniform registers), one elected lane issues
         const uint32_t a = smem_u32(sA + s * kTileBytes), b = smem_u32(sB + s * kTileBytes);
 #pragma unroll
         for (int k = 0; k < TBK / 8; k++) {
@@ -121,10 +122,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                        : smem_desc(a + k * 1024, TBK * 128, 512, kLayoutSw128Base32);
           const uint64_t bd = B_KMAJOR ? smem_desc(b + k * 32, 0, 1024, kLayoutSw128)
                                        : smem_desc(b + k * 1024, TBK * 128, 512, kLayoutSw128Base32);
-          mma_tf32(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          if (elect_one()) mma_tf32(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
-        tc_commit(empty + s);                   // frees the smem stage when these MMAs retire
-        if (kb == kb1 - 1) tc_commit(tmem_full);  // accumulator complete
+        if (elect_one()) {
+          tc_commit(empty + s);                   // frees the smem stage when these MMAs retire
+          if (kb == kb1 - 1) tc_commit(tmem_full);  // accumulator complete
+        }
       }
       __syncwarp();
     }

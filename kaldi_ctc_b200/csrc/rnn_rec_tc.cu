@@ -2,9 +2,11 @@
 //
 // One thread-block cluster per (direction, batch chunk).  CTA c of the cluster owns
 // the hidden units [32c, 32c+32): its 128 gate rows (row = 4*unit + gate; unused
-// gate slots of GRU / plain RNN are zero rows) of the recurrent matrix R stay in
-// shared memory as BF16 for all T steps, laid out as a K-major, 128-byte-swizzled
-// UMMA operand.  Per time step:
+// gate slots of GRU / plain RNN are zero rows) of the recurrent matrix R stay ON
+// CHIP as BF16 for all T steps -- in TENSOR MEMORY, as the A operand of
+// tcgen05.mma (lane = gate row, H/2 columns), so a step does not re-read 80 KB of
+// weights through the shared-memory port (measured: 1540 -> ~300 cycles of MMA issue
+// per step).  Per time step:
 //   MMA warp     waits until every CTA's slice of h_{t-1} has landed in the local
 //                (double-buffered, swizzled) h tile, then one elected lane issues
 //                H/16 tcgen05.mma (M=128, N=16, K=16, kind::f16/BF16) accumulating
@@ -14,12 +16,13 @@
 //                projection (prefetched from HBM one step ahead), apply the gate
 //                non-linearity, 4x4 quad transposes by warp shuffle so that one
 //                thread holds all gates of a (unit, utterance), fp32 cell update
-//                (cell / hidden state live in registers), store y / gates / cell,
-//                pack h_t to BF16 and write the 16-byte chunks straight into every
-//                CTA's next h tile through distributed shared memory, then one
-//                remote mbarrier arrive per peer.
-// No cluster-wide barrier inside the loop: the only synchronisation is the
-// per-CTA "h tile full" mbarrier fed by remote arrives.
+//                (cell / hidden state live in registers), pack h_t to BF16 and
+//                st.async the 16-byte chunks straight into every CTA's next
+//                (swizzled) h tile through distributed shared memory -- each
+//                store completes bytes on the destination's "h tile full"
+//                mbarrier, so there is no fence, no barrier and no arrive on the
+//                critical path; y / gates / cell go to HBM afterwards.
+// No cluster-wide barrier inside the loop.
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
@@ -35,17 +38,15 @@ using namespace tc;
 
 constexpr int UT = 32;          // hidden units per CTA
 constexpr int NPAD = 16;        // MMA N (utterances per chunk, zero padded)
-constexpr int kThreads = 192;   // warp 0: spare/loader, warp 1: MMA, warps 2-5: epilogue
+constexpr int kThreads = 192;   // warp 0: spare, warp 1: MMA, warps 2-5: epilogue
+constexpr int kTmemCols = 256;  // D: columns [0,16); A (R slice): columns [32, 32 + H/2)
+constexpr int kACol = 32;       // (several independent accumulators were measured: no gain, the
+                                //  burst is issue-bound at ~24 cycles per MMA, tools/mma_bench.cu)
 
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
-  return r;
 }
 __device__ __forceinline__ void st_cluster_v4(uint32_t raddr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z),
@@ -105,7 +106,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // forward
 // ===========================================================================
 // smem: [Rs: nkb x 128 rows x 128 B][hs: 2 x nkb x 16 rows x 128 B][barriers]
-template <int MODE, int NJ>
+template <int MODE, int NJ, int NKB>
 __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
   constexpr int G = MODE == 2 ? 4 : (MODE == 3 ? 3 : 1);
   constexpr int BC = 4 * NJ;
@@ -115,75 +116,107 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
   const int dir = blockIdx.y % a.dirs, chunk = blockIdx.y / a.dirs;
   const int b_lo = chunk * BC, nb = min(BC, a.B - b_lo);
   const int H = a.H, T = a.T, B = a.B, GH = G * H, HO = H * a.dirs;
-  const int nkb = H / 64;
+  const int nkb = NKB > 0 ? NKB : H / 64;  // NKB > 0: compile-time K extent, MMA loop fully unrolled
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   extern __shared__ uint8_t smem_dyn[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  uint8_t *Rs = smem;
-  uint8_t *hs = Rs + (size_t)nkb * 16384;             // two buffers of nkb * 2048 B
+  uint8_t *hs = smem;                                 // two buffers of nkb * 2048 B
   const int hs_bytes = nkb * 2048;
   uint64_t *hfull = reinterpret_cast<uint64_t *>(hs + 2 * hs_bytes);  // [2]
   uint64_t *acc_full = hfull + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
 
-  // ---- one-time set-up: R slice -> BF16, swizzled K-major; zero h tiles
-  {
-    const float *Rg = a.w_rec[dir];
-    for (int idx = tid; idx < 128 * H; idx += kThreads) {
-      const int k = idx % H, row = idx / H;
-      const int u = row >> 2, g = row & 3;
-      const float v = g < G ? Rg[((size_t)g * H + crank * UT + u) * H + k] : 0.f;
-      const int kb = k >> 6, kk = k & 63;
-      const uint32_t off = kb * 16384 + row * 128 + (((kk >> 3) ^ (row & 7)) << 4) + (kk & 7) * 2;
-      *reinterpret_cast<__nv_bfloat16 *>(Rs + off) = __float2bfloat16_rn(v);
-    }
-    for (int idx = tid; idx < 2 * hs_bytes / 16; idx += kThreads)
-      reinterpret_cast<uint4 *>(hs)[idx] = make_uint4(0, 0, 0, 0);
-  }
+  // bytes every CTA's h tile receives per step: NC slices of (BC rows x 32 units x 2 B)
+  const uint32_t h_bytes = (uint32_t)NC * BC * 64u;
+  for (int idx = tid; idx < 2 * hs_bytes / 16; idx += kThreads)
+    reinterpret_cast<uint4 *>(hs)[idx] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
-    mbar_init(hfull + 0, NC);
-    mbar_init(hfull + 1, NC);
+    mbar_init(hfull + 0, 1);
+    mbar_init(hfull + 1, 1);
     mbar_init(acc_full, 1);
     fence_barrier_init();
+    // arm both h tiles for their first fill (st.async completes bytes on them)
+    mbar_expect_tx(hfull + 0, h_bytes);
+    mbar_expect_tx(hfull + 1, h_bytes);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 32);
+    tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
-  fence_proxy_async_all();  // generic smem writes above -> visible to the tensor core (async proxy)
+  fence_proxy_async_all();  // zeroed h tiles -> visible to the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // ---- one-time: my 128 gate rows of R -> BF16 -> tensor memory (lane = row, column = k/2)
+  if (warp >= 2) {
+    const int q = warp & 3, row = q * 32 + lane;
+    const int u = row >> 2, g = row & 3;
+    const float *src = a.w_rec[dir] + ((size_t)(g < G ? g : 0) * H + crank * UT + u) * H;
+    for (int c0 = 0; c0 < H / 2; c0 += 16) {
+      uint32_t v[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const float2 f = *reinterpret_cast<const float2 *>(src + 2 * (c0 + i));
+        v[i] = g < G ? pack_bf16(f.x, f.y) : 0u;
+      }
+      tmem_st_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + kACol + c0, v);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
   cluster.sync();  // every CTA's tiles and barriers exist before anyone writes remotely
 
   if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = instr_desc(kFmtBF16, 0, 0, 128, NPAD);
-    const uint32_t rs0 = smem_u32(Rs), hs0 = smem_u32(hs);
+    // warp-uniform copies (shuffle from lane 0) so the compiler keeps MMA operands in uniform registers
+    const uint32_t hs0 = __shfl_sync(0xffffffffu, smem_u32(hs), 0);
+    const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const bool prof = a.dbg != nullptr && crank == 0 && blockIdx.y == 0;
+    long long pm[3] = {0, 0, 0};
     for (int step = 0; step < T; step++) {
       const int p = step & 1;
+      const long long m0 = prof ? clock64() : 0;
       if (step > 0) {
         const int use = p ? (step - 1) >> 1 : (step >> 1) - 1;
-        mbar_wait_cluster(hfull + p, use & 1);
+        mbar_wait(hfull + p, use & 1);
+        if (elect_one()) mbar_expect_tx(hfull + p, h_bytes);  // re-arm for the fill two steps ahead
       }
-      fence_proxy_async_all();
+      const long long m1 = prof ? clock64() : 0;
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t hb = hs0 + p * hs_bytes;
-        for (int kb = 0; kb < nkb; kb++) {
+      const long long m2 = prof ? clock64() : 0;
+      {
+        // warp-uniform issue: every lane computes the (uniform) descriptors, one elected lane
+        // issues -- keeps the operands in uniform registers (no per-MMA R2UR/ELECT loop)
+        // descriptor of the first K slice; later slices only add to the 14-bit address field
+        const uint64_t bd0 = smem_desc(hs0 + p * hs_bytes, 0, 1024, kLayoutSw128);
+        if (NKB > 0) {
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const uint64_t ad = smem_desc(rs0 + kb * 16384 + k * 32, 0, 1024, kLayoutSw128);
-            const uint64_t bd = smem_desc(hb + kb * 2048 + k * 32, 0, 1024, kLayoutSw128);
-            mma_bf16(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+          for (int kk = 0; kk < NKB * 4; kk++) {
+            const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * 2048 + (kk & 3) * 32) >> 4);
+            if (elect_one())
+              mma_bf16_ts(tmem_d, tmem_d + kACol + kk * 8, bd, idesc, kk ? 1u : 0u);
+          }
+        } else {
+          for (int kk = 0; kk < nkb * 4; kk++) {
+            const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * 2048 + (kk & 3) * 32) >> 4);
+            if (elect_one())
+              mma_bf16_ts(tmem_d, tmem_d + kACol + kk * 8, bd, idesc, kk ? 1u : 0u);
           }
         }
-        tc_commit(acc_full);
+        if (elect_one()) tc_commit(acc_full);
       }
       __syncwarp();
+      if (prof) {
+        const long long m3 = clock64();
+        pm[0] += m1 - m0; pm[1] += m2 - m1; pm[2] += m3 - m2;
+      }
     }
+    if (prof && lane == 0) { a.dbg[8] = pm[0]; a.dbg[9] = pm[1]; a.dbg[10] = pm[2]; }
   } else if (warp >= 2) {
     // ===================== epilogue =====================
     const int q = warp & 3;                  // TMEM lane quarter
@@ -212,29 +245,42 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
     load_pre(0);
 
     // remote addresses that never change
-    const uint32_t hs0 = smem_u32(hs), hf0 = smem_u32(hfull);
     const int kb_mine = crank >> 1, chunk_mine = (crank & 1) * 4 + q;
     const int peer_a = lane >> 2, peer_b = (lane >> 2) + 8;  // the two peers this lane serves
+    // cluster addresses of the peers' h tiles / barriers (the offset inside a CTA is the same everywhere)
+    const uint32_t rhs_a = mapa_u32(smem_u32(hs), peer_a < NC ? peer_a : 0);
+    const uint32_t rhs_b = mapa_u32(smem_u32(hs), peer_b < NC ? peer_b : 0);
+    const uint32_t rhf_a = mapa_u32(smem_u32(hfull), peer_a < NC ? peer_a : 0);
+    const uint32_t rhf_b = mapa_u32(smem_u32(hfull), peer_b < NC ? peer_b : 0);
 
+    const bool prof = a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == 2;
+    long long pe[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int step = 0; step < T; step++) {
       const int t = dir ? T - 1 - step : step;
+      const long long c0 = prof ? clock64() : 0;
       mbar_wait(acc_full, step & 1);
       tc_fence_after();
-      uint32_t r[16];
-      tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16), r);
+      const long long c1 = prof ? clock64() : 0;
+      uint32_t ra[16];
+      tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16), ra);
       tmem_ld_wait();
       tc_fence_before();
+      float r[BC];
+#pragma unroll
+      for (int e = 0; e < BC; e++) r[e] = __uint_as_float(ra[e]);
+      const long long c2 = prof ? clock64() : 0;
 
-      float hnew[NJ];
+      // ---- gates -> (unit, batch) threads, cell update; results kept in registers
+      float hnew[NJ], sv[NJ][4], sc[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; j++) {
         float x[4], g[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-          const float v = __uint_as_float(r[4 * j + e]) + pre[4 * j + e];
+          const float v = r[4 * j + e] + pre[4 * j + e];
           if (MODE == 2) {
-            const float sc = s == 2 ? 1.f : 0.5f;
-            const float th = tanh_fast(sc * v);
+            const float scl = s == 2 ? 1.f : 0.5f;
+            const float th = tanh_fast(scl * v);
             x[e] = s == 2 ? th : fmaf(0.5f, th, 0.5f);
           } else if (MODE == 3) {
             const float th = tanh_fast(0.5f * v);
@@ -244,41 +290,36 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
           }
         }
         quad_transpose(x, g, s);
-        const int b = 4 * j + s;
-        const bool valid = b < nb;
-        const size_t row = (size_t)t * B + b_lo + b;
+        const bool valid = 4 * j + s < nb;
         float h;
         if (MODE == 2) {
           cst[j] = fmaf(g[1], cst[j], g[0] * g[2]);
           h = g[3] * tanh_fast(cst[j]);
-          if (valid && a.save) {
-            float *gp = gates + row * GH + unit;
-            gp[0] = g[0]; gp[H] = g[1]; gp[2 * H] = g[2]; gp[3 * H] = g[3];
-            cell[row * H + unit] = cst[j];
-          }
+          sv[j][0] = g[0]; sv[j][1] = g[1]; sv[j][2] = g[2]; sv[j][3] = g[3];
+          sc[j] = cst[j];
         } else if (MODE == 3) {
           const float n = tanh_fast(fmaf(g[0], g[2], g[3]));
           h = fmaf(g[1], hst[j] - n, n);  // (1-z) n + z h_prev
-          if (valid && a.save) {
-            float *gp = gates + row * GH + unit;
-            gp[0] = g[0]; gp[H] = g[1]; gp[2 * H] = n;
-            cell[row * H + unit] = g[2];
-          }
+          sv[j][0] = g[0]; sv[j][1] = g[1]; sv[j][2] = n; sv[j][3] = 0.f;
+          sc[j] = g[2];
         } else {
           h = g[0];
-          if (valid && a.save) gates[row * GH + unit] = h;
+          sv[j][0] = h; sv[j][1] = sv[j][2] = sv[j][3] = 0.f;
+          sc[j] = 0.f;
         }
         if (!valid) h = 0.f;
         hst[j] = h;
         hnew[j] = h;
-        if (valid) a.y[row * HO + dir * H + unit] = h;
       }
 
+      const long long c3 = prof ? clock64() : 0;
+      long long c4 = c3, c5 = c3, c6 = c3;
+      // ---- critical path first: ship h_t to every CTA, then signal
       if (step + 1 < T) {
-        // ---- pack 8 consecutive units (one warp) of batch 4j+s into one 16-byte chunk
         const int pn = (step + 1) & 1;
 #pragma unroll
         for (int j = 0; j < NJ; j++) {
+          // pack 8 consecutive units (one warp) of batch 4j+s into one 16-byte chunk
           const float v = hnew[j];
           const float pv = __shfl_xor_sync(0xffffffffu, v, 4);
           const uint32_t pair = (lane & 4) ? pack_bf16(pv, v) : pack_bf16(v, pv);
@@ -291,22 +332,44 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
           else ch = make_uint4(lo, hi, lo2, hi2);
           const int b = 4 * j + s;
           const uint32_t off = pn * hs_bytes + kb_mine * 2048 + b * 128 + ((chunk_mine ^ (b & 7)) << 4);
-          if (peer_a < NC) st_cluster_v4(mapa_u32(hs0 + off, peer_a), ch);
-          if (peer_b < NC) st_cluster_v4(mapa_u32(hs0 + off, peer_b), ch);
+          if (peer_a < NC) st_async_v4(rhs_a + off, ch.x, ch.y, ch.z, ch.w, rhf_a + pn * 8);
+          if (peer_b < NC) st_async_v4(rhs_b + off, ch.x, ch.y, ch.z, ch.w, rhf_b + pn * 8);
         }
-        fence_proxy_async_all();
-        load_pre(step + 1);
-        epi_bar_sync();  // all 128 epilogue threads have issued their remote stores
-        if (warp == 2 && lane < NC) mbar_arrive_remote(mapa_u32(hf0 + pn * 8, lane));
+        if (prof) c4 = c5 = c6 = clock64();
+      }
+
+      // ---- off the critical path: results to HBM, next step's projection prefetch
+#pragma unroll
+      for (int j = 0; j < NJ; j++) {
+        const int b = 4 * j + s;
+        if (b < nb) {
+          const size_t row = (size_t)t * B + b_lo + b;
+          a.y[row * HO + dir * H + unit] = hnew[j];
+          if (a.save) {
+            float *gp = gates + row * GH + unit;
+            gp[0] = sv[j][0];
+            if (G > 1) { gp[H] = sv[j][1]; gp[2 * H] = sv[j][2]; }
+            if (G > 3) gp[3 * H] = sv[j][3];
+            if (MODE >= 2) cell[row * H + unit] = sc[j];
+          }
+        }
+      }
+      if (step + 1 < T) load_pre(step + 1);
+      if (prof) {
+        const long long c7 = clock64();
+        pe[0] += c1 - c0; pe[1] += c2 - c1; pe[2] += c3 - c2; pe[3] += c4 - c3;
+        pe[4] += c5 - c4; pe[5] += c6 - c5; pe[6] += c7 - c6;
       }
     }
+    if (prof && lane == 0)
+      for (int i = 0; i < 7; i++) a.dbg[i] = pe[i];
   }
   tc_fence_before();
   __syncthreads();
   cluster.sync();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 32);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -334,15 +397,22 @@ cudaError_t launch_cluster(K kernel, const RecArgs &a, size_t smem, cudaStream_t
   return cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
-size_t fwd_smem_bytes(int H) { return 1024 + (size_t)(H / 64) * (16384 + 2 * 2048) + 64; }
+size_t fwd_smem_bytes(int H) { return 1024 + (size_t)(H / 64) * (2 * 2048) + 64; }
 
 template <int MODE>
 cudaError_t launch_fwd(const RecArgs &a, cudaStream_t stream) {
   const size_t smem = fwd_smem_bytes(a.H);
+  if (a.H == 320) {  // the benchmark width: K extent known at compile time
+    switch (a.BC) {
+      case 4: return launch_cluster(rec_tc_fwd_kernel<MODE, 1, 5>, a, smem, stream);
+      case 8: return launch_cluster(rec_tc_fwd_kernel<MODE, 2, 5>, a, smem, stream);
+      default: return launch_cluster(rec_tc_fwd_kernel<MODE, 4, 5>, a, smem, stream);
+    }
+  }
   switch (a.BC) {
-    case 4: return launch_cluster(rec_tc_fwd_kernel<MODE, 1>, a, smem, stream);
-    case 8: return launch_cluster(rec_tc_fwd_kernel<MODE, 2>, a, smem, stream);
-    default: return launch_cluster(rec_tc_fwd_kernel<MODE, 4>, a, smem, stream);
+    case 4: return launch_cluster(rec_tc_fwd_kernel<MODE, 1, 0>, a, smem, stream);
+    case 8: return launch_cluster(rec_tc_fwd_kernel<MODE, 2, 0>, a, smem, stream);
+    default: return launch_cluster(rec_tc_fwd_kernel<MODE, 4, 0>, a, smem, stream);
   }
 }
 
@@ -352,7 +422,7 @@ cudaError_t launch_fwd(const RecArgs &a, cudaStream_t stream) {
 // and at most 16 CTAs of 32 units per cluster.
 bool rec_tc_supported(int mode, int H) {
   (void)mode;
-  return H % 64 == 0 && H / UT <= 16 && fwd_smem_bytes(H) <= 227 * 1024;
+  return H % 64 == 0 && H / UT <= 16 && kACol + H / 2 <= kTmemCols;
 }
 
 // batch chunk: the smallest of {4, 8, 16} that keeps all clusters resident at once

@@ -1,0 +1,71 @@
+// Micro-benchmark: cycles for a burst of tcgen05.mma (M=128, K=16, bf16) as a function of N,
+// operand source (A from SMEM vs TMEM) and accumulator reuse.  Garbage data; timing only.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mma_bench tools/mma_bench.cu && ./mma_bench
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../kaldi_ctc_b200/csrc/tc_common.cuh"
+using namespace b200::tc;
+
+template <int N, bool TS, int NACC>
+__global__ void __launch_bounds__(128, 1) k(long long *out, int nmma, int reps) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+  asm volatile("fence.proxy.async;" ::: "memory");
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tm = __shfl_sync(0xffffffffu, slot, 0);
+  if (warp == 0) {
+    constexpr uint32_t idesc = instr_desc(kFmtBF16, 0, 0, 128, N);
+    const uint32_t a0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0), b0 = a0 + 32768;
+    long long tot = 0;
+    for (int r = 0; r < reps; r++) {
+      const long long t0 = clock64();
+      for (int kk = 0; kk < nmma; kk++) {
+        const uint64_t ad = smem_desc(a0 + (kk & 3) * 32 + (kk >> 2) * 16384 % 32768, 0, 1024, kLayoutSw128);
+        const uint64_t bd = smem_desc(b0 + (kk & 3) * 32, 0, 1024, kLayoutSw128);
+        const uint32_t d = tm + (kk % NACC) * N;
+        if (elect_one()) {
+          if (TS) mma_bf16_ts(d, tm + 256 + (kk % 20) * 8, bd, idesc, kk >= NACC);
+          else mma_bf16(d, ad, bd, idesc, kk >= NACC);
+        }
+      }
+      if (elect_one()) tc_commit(&bar);
+      __syncwarp();
+      mbar_wait(&bar, r & 1);
+      tot += clock64() - t0;
+    }
+    if (threadIdx.x == 0) out[0] = tot / reps;
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tm, 512); }
+}
+
+template <int N, bool TS, int NACC>
+void run(const char *name, long long *d) {
+  cudaFuncSetAttribute(k<N, TS, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 70000);
+  for (int nm : {1, 20, 40}) {
+    k<N, TS, NACC><<<1, 128, 70000>>>(d, nm, 50);
+    long long h = 0;
+    cudaError_t e = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+    printf("%-28s N=%3d nmma=%2d  cycles=%lld  (%.1f / mma)  %s\n", name, N, nm, h, (double)h / nm, cudaGetErrorString(e));
+  }
+}
+
+int main() {
+  long long *d;
+  cudaMalloc(&d, 64);
+  run<16, false, 1>("SS 1acc", d);
+  run<16, true, 1>("TS 1acc", d);
+  run<16, true, 4>("TS 4acc", d);
+  run<32, true, 1>("TS 1acc", d);
+  run<64, true, 1>("TS 1acc", d);
+  run<128, true, 1>("TS 1acc", d);
+  run<128, false, 1>("SS 1acc", d);
+  run<256, false, 1>("SS 1acc", d);
+  return 0;
+}
