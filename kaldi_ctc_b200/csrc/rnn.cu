@@ -364,7 +364,12 @@ b200rnnStatus_t b200rnnBackwardData(b200rnnPlan_t p, int T, const float *y, cons
     }
     {
       Timed tm(p, 1, stream);
-      CK(rec_fp32_backward(a, stream));
+      if (p->tcNC && !getenv("B200RNN_TC_NO_BWD")) {
+        a.NC = p->tcNC; a.U = 32; a.BC = p->tcBC;
+        CK(rec_tc_backward(a, stream));
+      } else {
+        CK(rec_fp32_backward(a, stream));
+      }
     }
     p->launches++;
     if (dxl) {

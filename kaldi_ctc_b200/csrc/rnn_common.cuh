@@ -85,5 +85,6 @@ int rec_fp32_pick_cluster(int mode, int H);
 bool rec_tc_supported(int mode, int H);
 int rec_tc_pick_chunk(int H, int B, int dirs);
 cudaError_t rec_tc_forward(const RecArgs &a, cudaStream_t stream);  // a.NC = H/32, a.BC in {4,8,16}
+cudaError_t rec_tc_backward(const RecArgs &a, cudaStream_t stream);
 
 }  // namespace b200

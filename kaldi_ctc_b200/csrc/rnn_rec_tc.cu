@@ -373,6 +373,273 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
   }
 }
 
+// ===========================================================================
+// backward (data): gate gradients for all steps + the dh recurrence
+// ===========================================================================
+// CTA c keeps R_slice^T (its 128 gate rows, all H columns) in tensor memory as the A
+// operand: M = hidden index k (H padded to MT tiles of 128 lanes), K = own gate row r.
+// Per step:  epilogue threads (unit, utterance) form dh = dy + sum of the partial
+// products received from every CTA, compute the gate gradients (fp32), write them
+// to HBM (for the dW/dx GEMMs) and as BF16 into the swizzled [utterance][gate row]
+// B tile; the MMA warp issues MT*8 tcgen05.mma giving the PARTIAL dh_{prev}[k][b]
+// of this CTA's rows for ALL k; each epilogue warp then st.async's its 32 lanes
+// (= the 32 units of exactly one peer CTA) into that peer's receive buffer: a
+// reduce-scatter over distributed shared memory, completion counted on the
+// peer's mbarrier.
+template <int MODE, int NJ>
+__global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
+  constexpr int G = MODE == 2 ? 4 : (MODE == 3 ? 3 : 1);
+  constexpr int BC = 4 * NJ;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int NC = a.NC;
+  const int dir = blockIdx.y % a.dirs, chunk = blockIdx.y / a.dirs;
+  const int b_lo = chunk * BC, nb = min(BC, a.B - b_lo);
+  const int H = a.H, T = a.T, B = a.B, GH = G * H, HO = H * a.dirs;
+  const int MT = (H + 127) / 128;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t tmem_cols = 64 + MT * 64 <= 256 ? 256u : 512u;
+
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint8_t *dgs = smem;                                              // 2 k-blocks x [16 rows x 128 B]
+  float *recv = reinterpret_cast<float *>(smem + 4096);            // [2][NC][32][BC]
+  const int recv_floats = NC * 32 * BC;
+  uint64_t *rfull = reinterpret_cast<uint64_t *>(smem + 4096 + 2 * recv_floats * 4);  // [2]
+  uint64_t *acc_full = rfull + 2;
+  uint64_t *dg_ready = acc_full + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(dg_ready + 1);
+  const uint32_t r_bytes = (uint32_t)recv_floats * 4u;  // bytes one step delivers into a receive buffer
+
+  for (int idx = tid; idx < 4096 / 16; idx += kThreads) reinterpret_cast<uint4 *>(dgs)[idx] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(rfull + 0, 1);
+    mbar_init(rfull + 1, 1);
+    mbar_init(acc_full, 1);
+    mbar_init(dg_ready, 128);
+    fence_barrier_init();
+    mbar_expect_tx(rfull + 0, r_bytes);
+    mbar_expect_tx(rfull + 1, r_bytes);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  fence_proxy_async_all();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // ---- one-time: R_slice^T -> BF16 -> tensor memory.  lane = k within the tile, column c = rows 2c, 2c+1
+  if (warp >= 2) {
+    const int q = warp & 3;
+    const float *Rg = a.w_rec[dir];
+    for (int m = 0; m < MT; m++) {
+      const int k = m * 128 + q * 32 + lane;
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t v[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const int r0 = 2 * (c0 + i);  // rows r0 = 4u+g, r0+1 = 4u+g+1 (same unit)
+          const int u = r0 >> 2, g0 = r0 & 3;
+          float f0 = 0.f, f1 = 0.f;
+          if (k < H) {
+            if (g0 < G) f0 = Rg[((size_t)g0 * H + crank * UT + u) * H + k];
+            if (g0 + 1 < G) f1 = Rg[((size_t)(g0 + 1) * H + crank * UT + u) * H + k];
+          }
+          v[i] = pack_bf16(f0, f1);
+        }
+        tmem_st_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + 64 + m * 64 + c0, v);
+      }
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster.sync();
+
+  if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = instr_desc(kFmtBF16, 0, 0, 128, NPAD);
+    const uint32_t dg0 = __shfl_sync(0xffffffffu, smem_u32(dgs), 0);
+    const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint64_t bd0 = smem_desc(dg0, 0, 1024, kLayoutSw128);
+    for (int step = 0; step + 1 < T; step++) {
+      mbar_wait(dg_ready, step & 1);
+      tc_fence_after();
+      for (int m = 0; m < MT; m++) {
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) {
+          const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * 2048 + (kk & 3) * 32) >> 4);
+          if (elect_one()) mma_bf16_ts(tmem_d + m * NPAD, tmem_d + 64 + m * 64 + kk * 8, bd, idesc, kk ? 1u : 0u);
+        }
+      }
+      if (elect_one()) tc_commit(acc_full);
+      __syncwarp();
+    }
+  } else if (warp >= 2) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int s = lane & 3;
+    const int ul = q * 8 + (lane >> 2);
+    const int unit = crank * UT + ul;
+    float *gates = a.gates[dir];
+    float *cell = a.cell[dir];
+    float carry[NJ];  // LSTM: dc carried to the previous step; GRU: dh * z
+#pragma unroll
+    for (int j = 0; j < NJ; j++) carry[j] = 0.f;
+
+    // operands of the step, prefetched one step ahead
+    float pdy[NJ], pg[NJ][G], pc[NJ], pcp[NJ];
+    auto load_step = [&](int step) {
+      const int fstep = T - 1 - step;
+      const int t = dir ? T - 1 - fstep : fstep;
+      const int tp = dir ? t + 1 : t - 1;
+#pragma unroll
+      for (int j = 0; j < NJ; j++) {
+        const int b = 4 * j + s;
+        pdy[j] = 0.f;
+        pc[j] = pcp[j] = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; g++) pg[j][g] = 0.f;
+        if (b < nb) {
+          const size_t row = (size_t)t * B + b_lo + b;
+          pdy[j] = a.dy[row * HO + dir * H + unit];
+#pragma unroll
+          for (int g = 0; g < G; g++) pg[j][g] = gates[row * GH + (size_t)g * H + unit];
+          if (MODE >= 2) pc[j] = cell[row * H + unit];
+          if (fstep > 0) {
+            const size_t rowp = (size_t)tp * B + b_lo + b;
+            if (MODE == 2) pcp[j] = cell[rowp * H + unit];
+            if (MODE == 3) pcp[j] = a.y[rowp * HO + dir * H + unit];
+          }
+        }
+      }
+    };
+    load_step(0);
+
+    // destination of my TMEM lanes' partial sums: for tile m, lanes of this warp are the 32
+    // units of CTA 4m+q; inside its receive buffer: [parity][src = crank][lane][b]
+    uint32_t rdst[4], rbar[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      const int tgt = 4 * m + q;
+      const int ok = m < MT && tgt < NC;
+      rdst[m] = mapa_u32(smem_u32(recv) + (uint32_t)((crank * 32 + lane) * BC) * 4u, ok ? tgt : 0);
+      rbar[m] = mapa_u32(smem_u32(rfull), ok ? tgt : 0);
+    }
+
+    for (int step = 0; step < T; step++) {
+      const int fstep = T - 1 - step;
+      const int t = dir ? T - 1 - fstep : fstep;
+      const int p = step & 1;
+      // ---- dh arriving from the step processed before (frame t +- 1)
+      float dhr[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; j++) dhr[j] = 0.f;
+      if (step > 0) {
+        const int use = p ? (step - 1) >> 1 : (step >> 1) - 1;
+        mbar_wait(rfull + p, use & 1);
+        // re-arm at once: the next fill of this buffer is two steps away
+        if (warp == 2 && lane == 0) mbar_expect_tx(rfull + p, r_bytes);
+        const float *rc = recv + (size_t)p * recv_floats;
+        for (int src = 0; src < NC; src++) {
+#pragma unroll
+          for (int j = 0; j < NJ; j++) dhr[j] += rc[(src * 32 + ul) * BC + 4 * j + s];
+        }
+      }
+      // ---- gate gradients of (unit, batch 4j+s)
+      float dgv[NJ][4], dq[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; j++) {
+        float dh = pdy[j] + dhr[j];
+        dgv[j][0] = dgv[j][1] = dgv[j][2] = dgv[j][3] = 0.f;
+        dq[j] = 0.f;
+        if (MODE == 2) {
+          const float i = pg[j][0], f = pg[j][1 % G], g_ = pg[j][2 % G], o = pg[j][3 % G];
+          const float tc_ = tanh_fast(pc[j]);
+          const float dc = fmaf(dh * o, 1.f - tc_ * tc_, carry[j]);
+          dgv[j][0] = dc * g_ * i * (1.f - i);
+          dgv[j][1] = dc * pcp[j] * f * (1.f - f);
+          dgv[j][2] = dc * i * (1.f - g_ * g_);
+          dgv[j][3] = dh * tc_ * o * (1.f - o);
+          carry[j] = dc * f;
+        } else if (MODE == 3) {
+          dh += carry[j];
+          const float r = pg[j][0], z = pg[j][1 % G], n = pg[j][2 % G], qv = pc[j];
+          const float dn = dh * (1.f - z) * (1.f - n * n);
+          dgv[j][0] = dn * qv * r * (1.f - r);
+          dgv[j][1] = dh * (pcp[j] - n) * z * (1.f - z);
+          dgv[j][2] = dn;       // input side of the n gate
+          dq[j] = dn * r;       // recurrent side
+          carry[j] = dh * z;
+        } else {
+          const float h = pg[j][0];
+          dgv[j][0] = dh * (MODE == 0 ? (h > 0.f ? 1.f : 0.f) : (1.f - h * h));
+        }
+        if (4 * j + s >= nb) {
+          dgv[j][0] = dgv[j][1] = dgv[j][2] = dgv[j][3] = 0.f;
+          dq[j] = 0.f;
+          carry[j] = 0.f;
+        }
+      }
+      if (step + 1 < T) {
+        // ---- recurrent-side gradients -> BF16 B tile [utterance row][gate row r = 4*ul + g]
+#pragma unroll
+        for (int j = 0; j < NJ; j++) {
+          const int b = 4 * j + s;
+          const float g2 = MODE == 3 ? dq[j] : dgv[j][2];
+          const uint2 v = make_uint2(pack_bf16(dgv[j][0], dgv[j][1]), pack_bf16(g2, dgv[j][3]));
+          const uint32_t off = (ul >> 4) * 2048 + b * 128 + ((((ul & 15) >> 1) ^ (b & 7)) << 4) + (ul & 1) * 8;
+          *reinterpret_cast<uint2 *>(dgs + off) = v;
+        }
+        fence_proxy_async();  // my generic smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(dg_ready);
+      }
+      // ---- off the critical path: gradients to HBM, operands of the next step
+#pragma unroll
+      for (int j = 0; j < NJ; j++) {
+        const int b = 4 * j + s;
+        if (b < nb) {
+          const size_t row = (size_t)t * B + b_lo + b;
+          float *gp = gates + row * GH + unit;
+          gp[0] = dgv[j][0];
+          if (G > 1) { gp[H] = dgv[j][1]; gp[2 * H] = dgv[j][2]; }
+          if (G > 3) gp[3 * H] = dgv[j][3];
+          if (MODE == 3) cell[row * H + unit] = dq[j];
+        }
+      }
+      if (step + 1 < T) {
+        // my (unit, batch) operands of the next step are not touched by anyone else: safe to prefetch now
+        load_step(step + 1);
+        // ---- partial dh_{prev} of my rows, for all k: scatter to the owners
+        mbar_wait(acc_full, step & 1);
+        tc_fence_after();
+        const int pn = (step + 1) & 1;
+        for (int m = 0; m < MT; m++) {
+          uint32_t r[16];
+          tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + m * NPAD, r);
+          tmem_ld_wait();
+          if (4 * m + q < NC) {
+            const uint32_t dst = rdst[m] + (uint32_t)pn * r_bytes, bar = rbar[m] + pn * 8;
+#pragma unroll
+            for (int j = 0; j < NJ; j++) st_async_v4(dst + j * 16, r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3], bar);
+          }
+        }
+        tc_fence_before();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster.sync();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 template <typename K>
 cudaError_t launch_cluster(K kernel, const RecArgs &a, size_t smem, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -416,6 +683,18 @@ cudaError_t launch_fwd(const RecArgs &a, cudaStream_t stream) {
   }
 }
 
+size_t bwd_smem_bytes(int H, int BC) { return 1024 + 4096 + (size_t)2 * (H / UT) * 32 * BC * 4 + 64; }
+
+template <int MODE>
+cudaError_t launch_bwd(const RecArgs &a, cudaStream_t stream) {
+  const size_t smem = bwd_smem_bytes(a.H, a.BC);
+  switch (a.BC) {
+    case 4: return launch_cluster(rec_tc_bwd_kernel<MODE, 1>, a, smem, stream);
+    case 8: return launch_cluster(rec_tc_bwd_kernel<MODE, 2>, a, smem, stream);
+    default: return launch_cluster(rec_tc_bwd_kernel<MODE, 4>, a, smem, stream);
+  }
+}
+
 }  // namespace
 
 // The tcgen05 kernels need H a multiple of 64 (whole 128-byte swizzle rows of BF16)
@@ -440,6 +719,16 @@ cudaError_t rec_tc_forward(const RecArgs &a, cudaStream_t stream) {
     case 1: return launch_fwd<1>(a, stream);
     case 2: return launch_fwd<2>(a, stream);
     default: return launch_fwd<3>(a, stream);
+  }
+}
+
+cudaError_t rec_tc_backward(const RecArgs &a, cudaStream_t stream) {
+  if (!rec_tc_supported(a.mode, a.H) || a.NC != a.H / UT) return cudaErrorInvalidValue;
+  switch (a.mode) {
+    case 0: return launch_bwd<0>(a, stream);
+    case 1: return launch_bwd<1>(a, stream);
+    case 2: return launch_bwd<2>(a, stream);
+    default: return launch_bwd<3>(a, stream);
   }
 }
 
