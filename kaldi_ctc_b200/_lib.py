@@ -25,7 +25,7 @@ def load(name):
             raise LibraryMissing(
                 "%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(or make -C kaldi_ctc_b200/csrc). There is no CPU fallback." % p)
-        _cache[name] = ctypes.CDLL(p, mode=ctypes.RTLD_GLOBAL)
+        _cache[name] = ctypes.CDLL(p)  # RTLD_LOCAL: libb200cudnn.so exports cuDNN names, keep them private
     return _cache[name]
 
 

@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADERS = {
     "libb200ctc.so": ["include/ctc.h", "include/b200ctc.h"],
     "libb200rnn.so": ["include/b200rnn.h"],
+    "libb200cudnn.so": ["include/cudnn_v5_compat/cudnn.h"],
 }
 
 
