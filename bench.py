@@ -58,7 +58,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(f)
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
         if not self.samples:
@@ -117,6 +117,40 @@ def cpu_baseline(spec, blobs, aw, ab, frames=96):
     dt = time.perf_counter() - t0
     return {"value": float(T.sum()) / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "1 step of %d utts x %d frames (same model, fp32 OpenMP restatement)" % (B, frames)}
+
+
+def ctc_roofline(dev, pk, pk_src):
+    """Second half of BASELINE.json's metric: CTC loss+grad HBM GB/s.  configs[4] (A=4000, T<=3000, L 50-600)
+    at 32 utterances (one GPU's share of the 256 at 8 GPUs), algorithmic bytes of BASELINE.md section 3,
+    CUDA events around the three kernels of one b200ctc_loss call, L2 flushed between calls."""
+    import torch
+    from kaldi_ctc_b200 import ctc, synth
+    bt = synth.config_ctc(5, scale=0.125)
+    op = ctc.CtcLoss(dev)
+    a = torch.from_numpy(bt.activations).to(dev)
+    g = torch.empty_like(a)
+    cd = torch.zeros(a.shape[1], device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    run = lambda: op.compute_extended(a, bt.flat_labels, bt.label_lengths, bt.input_lengths, gradients=g,
+                                      costs_dev=cd, no_sync=True)
+    for _ in range(3):
+        run()
+    ts = []
+    for _ in range(5):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    nbytes = ctc.algorithmic_bytes(bt.label_lengths, bt.input_lengths, a.shape[2])
+    ach = nbytes / ms / 1e6
+    return {"workload": "configs[4] slice: A=4000, B=32, T_b~U{1500..3000}, L_b~U{50..600}", "bound": "hbm",
+            "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+            "ms_per_call": ms, "algorithmic_bytes": int(nbytes), "peak_source": pk_src, "traffic": None,
+            "l2": "256 MB flush between calls"}
 
 
 def run_b200(args, rank, local_rank, world):
@@ -218,6 +252,10 @@ def run_b200(args, rank, local_rank, world):
         "roofline": roofline,
         "objf_last_step": objf,
     }
+    if rank == 0 and world == 1 and not args.no_ctc_roofline:
+        del up
+        torch.cuda.empty_cache()
+        line["ctc_roofline"] = ctc_roofline(dev, pk, pk_src)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(spec, blobs, aw, ab)
@@ -232,9 +270,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--math", default=os.environ.get("B200_MATH", "fp32"), choices=["fp32", "tensor"])
+    ap.add_argument("--math", default=os.environ.get("B200_MATH", "tensor"), choices=["fp32", "tensor"])
     ap.add_argument("--ref-frames", type=int, default=64, help="frames per utterance of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ctc-roofline", action="store_true", help="skip the secondary CTC HBM-roofline measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -168,13 +168,12 @@ class NnetCtcUpdater:
         n = len(self.rnns)
         top_in = self.acts[-1][:rows]
         dp = update and self.world > 1
-        pending = []
         if dp:
-            import torch.distributed as dist
+            from .parallel import GradientReducer
+            red = GradientReducer()
             d = self.affine.Backprop(top_in, self.deriv[:rows], None, in_deriv=self.dact[0][:rows],
                                      grad_out=(self.gW, self.gb))
-            pending.append((dist.all_reduce(self.gW, async_op=True), None))
-            pending.append((dist.all_reduce(self.gb, async_op=True), "affine"))
+            red.submit([self.gW, self.gb], lambda: self.affine.Update(self.gW, self.gb))
         else:
             d = self.affine.Backprop(top_in, self.deriv[:rows], self.affine if update else None,
                                      in_deriv=self.dact[0][:rows])
@@ -185,16 +184,13 @@ class NnetCtcUpdater:
             if dp:
                 grab = _Grab()
                 d = comp.Backprop(inp, self.acts[l][:rows], d, to_update=grab, want_in_deriv=(l > 0))
-                pending.append((dist.all_reduce(comp.filter_params_grad_, async_op=True), comp))
+                red.submit([comp.filter_params_grad_],
+                           lambda c=comp: c.Update(c.filter_params_grad_, c.clip_gradient_))
             else:
                 d = comp.Backprop(inp, self.acts[l][:rows], d, to_update=comp if update else None,
                                   want_in_deriv=(l > 0))
-        for work, who in pending:
-            work.wait()
-            if who == "affine":
-                self.affine.Update(self.gW, self.gb)
-            elif who is not None:
-                who.Update(who.filter_params_grad_, who.clip_gradient_)
+        if dp:
+            red.finish()
         return d
 
     def ComputeForMinibatch(self, feats_host, T, flat_labels, label_lengths, input_lengths, update=True,
