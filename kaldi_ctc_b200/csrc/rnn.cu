@@ -315,16 +315,21 @@ b200rnnStatus_t b200rnnForward(b200rnnPlan_t p, int T, const float *x, const flo
         static long long *dbg = nullptr;
         const bool prof = getenv("B200RNN_TC_PROFILE") != nullptr;
         if (prof && !dbg) cudaMalloc(&dbg, 64 * sizeof(long long));
+        if (prof) cudaMemsetAsync(dbg, 0, 64 * sizeof(long long), stream);
         a.dbg = prof ? dbg : nullptr;
         CK(rec_tc_forward(a, stream));
         if (prof) {  // tuning aid: cycles per step of each phase (cluster 0, CTA 0)
-          long long h[16];
+          long long h[24];
           cudaStreamSynchronize(stream);
           cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
           const double n = T;
           fprintf(stderr, "[b200rnn fwd tc] cyc/step epilogue: wait_acc %.0f tmem_ld %.0f math %.0f pack+dsmem %.0f "
-                  "bar %.0f arrive %.0f gstore+prefetch %.0f | mma warp: wait_h %.0f fence %.0f issue %.0f\n",
-                  h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[8] / n, h[9] / n, h[10] / n);
+                  "bar %.0f arrive %.0f gstore+prefetch %.0f | mma warp: wait_h %.0f fence %.0f issue %.0f complete %.0f\n",
+                  h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[8] / n, h[9] / n, h[10] / n,
+                  h[11] / n);
+          fprintf(stderr, "[b200rnn fwd tc] issuer-complete -> epilogue-sees-acc %.0f cyc; h sent -> next h seen by issuer %.0f cyc\n",
+                  (h[13] - h[12]) / n, (h[14] - h[15]) / n + (double)(h[8] + h[9] + h[10] + h[11]) / n);
+          fprintf(stderr, "[b200rnn fwd tc] tcgen05.fence::after_thread_sync in the epilogue: %.0f cyc\n", h[16] / n);
         }
       } else {
         CK(rec_fp32_forward(a, stream));

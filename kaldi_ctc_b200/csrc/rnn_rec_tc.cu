@@ -26,6 +26,8 @@
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "rnn_common.cuh"
 #include "tc_common.cuh"
 
@@ -38,7 +40,7 @@ using namespace tc;
 
 constexpr int UT = 32;          // hidden units per CTA
 constexpr int NPAD = 16;        // MMA N (utterances per chunk, zero padded)
-constexpr int kThreads = 192;   // warp 0: spare, warp 1: MMA, warps 2-5: epilogue
+constexpr int kThreads = 192;   // warps 0,1: MMA issuers (one accumulator each), warps 2-5: epilogue
 constexpr int kTmemCols = 256;  // D: columns [0,16); A (R slice): columns [32, 32 + H/2)
 constexpr int kACol = 32;       // (several independent accumulators were measured: no gain, the
                                 //  burst is issue-bound at ~24 cycles per MMA, tools/mma_bench.cu)
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
   if (tid == 0) {
     mbar_init(hfull + 0, 1);
     mbar_init(hfull + 1, 1);
-    mbar_init(acc_full, 1);
+    mbar_init(acc_full, 2);  // one commit from each of the two issuing warps
     fence_barrier_init();
     // arm both h tiles for their first fill (st.async completes bytes on them)
     mbar_expect_tx(hfull + 0, h_bytes);
@@ -170,21 +172,26 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
   tc_fence_after();
   cluster.sync();  // every CTA's tiles and barriers exist before anyone writes remotely
 
-  if (warp == 1) {
-    // ===================== MMA issuer =====================
+  if (warp < 2) {
+    // ===================== MMA issuers =====================
+    // The burst of H/16 small MMAs is issue-bound (~30 cycles each), so two warps issue half of
+    // the K range each into their own accumulator (columns [16*warp, 16*warp+16)); the epilogue
+    // adds the two.  Warp 1 also re-arms the h-tile barrier.
     constexpr uint32_t idesc = instr_desc(kFmtBF16, 0, 0, 128, NPAD);
     // warp-uniform copies (shuffle from lane 0) so the compiler keeps MMA operands in uniform registers
     const uint32_t hs0 = __shfl_sync(0xffffffffu, smem_u32(hs), 0);
     const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const bool prof = a.dbg != nullptr && crank == 0 && blockIdx.y == 0;
-    long long pm[3] = {0, 0, 0};
+    const bool prof = a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == 1;
+    long long pm[4] = {0, 0, 0, 0};
     for (int step = 0; step < T; step++) {
       const int p = step & 1;
       const long long m0 = prof ? clock64() : 0;
       if (step > 0) {
         const int use = p ? (step - 1) >> 1 : (step >> 1) - 1;
         mbar_wait(hfull + p, use & 1);
-        if (elect_one()) mbar_expect_tx(hfull + p, h_bytes);  // re-arm for the fill two steps ahead
+        // re-arm for the fill two steps ahead (both issuers are past the wait before any such
+        // data can exist: it needs this step's h from every CTA first)
+        if (warp == 1 && elect_one()) mbar_expect_tx(hfull + p, h_bytes);
       }
       const long long m1 = prof ? clock64() : 0;
       tc_fence_after();
@@ -194,29 +201,39 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
         // issues -- keeps the operands in uniform registers (no per-MMA R2UR/ELECT loop)
         // descriptor of the first K slice; later slices only add to the 14-bit address field
         const uint64_t bd0 = smem_desc(hs0 + p * hs_bytes, 0, 1024, kLayoutSw128);
+        const uint32_t dacc = tmem_d + warp * NPAD;
         if (NKB > 0) {
 #pragma unroll
-          for (int kk = 0; kk < NKB * 4; kk++) {
+          for (int i = 0; i < NKB * 2; i++) {
+            const int kk = 2 * i + warp;  // even K slices: warp 0, odd: warp 1
             const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * 2048 + (kk & 3) * 32) >> 4);
-            if (elect_one())
-              mma_bf16_ts(tmem_d, tmem_d + kACol + kk * 8, bd, idesc, kk ? 1u : 0u);
+            if (elect_one()) mma_bf16_ts(dacc, tmem_d + kACol + kk * 8, bd, idesc, i ? 1u : 0u);
           }
         } else {
-          for (int kk = 0; kk < nkb * 4; kk++) {
+          for (int i = 0; i < nkb * 2; i++) {
+            const int kk = 2 * i + warp;
             const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * 2048 + (kk & 3) * 32) >> 4);
-            if (elect_one())
-              mma_bf16_ts(tmem_d, tmem_d + kACol + kk * 8, bd, idesc, kk ? 1u : 0u);
+            if (elect_one()) mma_bf16_ts(dacc, tmem_d + kACol + kk * 8, bd, idesc, i ? 1u : 0u);
           }
         }
         if (elect_one()) tc_commit(acc_full);
       }
       __syncwarp();
+      const long long m3 = prof ? clock64() : 0;
+      if (warp == 1) {
+        // hand the accumulator to the epilogue through a named barrier: the issuing warp sees the
+        // tcgen05.commit arrive ~60 cycles after its last MMA, warps sleeping on the mbarrier were
+        // measured to resume ~300 cycles later
+        mbar_wait(acc_full, step & 1);
+        asm volatile("bar.arrive 2, 160;" ::: "memory");
+      }
       if (prof) {
-        const long long m3 = clock64();
-        pm[0] += m1 - m0; pm[1] += m2 - m1; pm[2] += m3 - m2;
+        const long long m4 = clock64();
+        pm[0] += m1 - m0; pm[1] += m2 - m1; pm[2] += m3 - m2; pm[3] += m4 - m3;
+        if (lane == 0) { a.dbg[12] += m4; a.dbg[14] += m1; }  // absolute SM clocks: completion / h-arrival seen
       }
     }
-    if (prof && lane == 0) { a.dbg[8] = pm[0]; a.dbg[9] = pm[1]; a.dbg[10] = pm[2]; }
+    if (prof && lane == 0) { a.dbg[8] = pm[0]; a.dbg[9] = pm[1]; a.dbg[10] = pm[2]; a.dbg[11] = pm[3]; }
   } else if (warp >= 2) {
     // ===================== epilogue =====================
     const int q = warp & 3;                  // TMEM lane quarter
@@ -258,16 +275,18 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
     for (int step = 0; step < T; step++) {
       const int t = dir ? T - 1 - step : step;
       const long long c0 = prof ? clock64() : 0;
-      mbar_wait(acc_full, step & 1);
+      asm volatile("bar.sync 2, 160;" ::: "memory");
+      const long long c1a = prof ? clock64() : 0;
       tc_fence_after();
       const long long c1 = prof ? clock64() : 0;
-      uint32_t ra[16];
-      tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16), ra);
+      if (prof && lane == 0) a.dbg[16] += c1 - c1a;
+      uint32_t ra[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16), ra);
       tmem_ld_wait();
       tc_fence_before();
-      float r[BC];
+      float r[BC];  // the two issuers' partial sums
 #pragma unroll
-      for (int e = 0; e < BC; e++) r[e] = __uint_as_float(ra[e]);
+      for (int e = 0; e < BC; e++) r[e] = __uint_as_float(ra[e]) + __uint_as_float(ra[NPAD + e]);
       const long long c2 = prof ? clock64() : 0;
 
       // ---- gates -> (unit, batch) threads, cell update; results kept in registers
@@ -357,6 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
       if (step + 1 < T) load_pre(step + 1);
       if (prof) {
         const long long c7 = clock64();
+        if (lane == 0) { a.dbg[13] += c1; a.dbg[15] += c4; }      // accumulator seen by the epilogue / h sent
         pe[0] += c1 - c0; pe[1] += c2 - c1; pe[2] += c3 - c2; pe[3] += c4 - c3;
         pe[4] += c5 - c4; pe[5] += c6 - c5; pe[6] += c7 - c6;
       }
@@ -415,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
   if (tid == 0) {
     mbar_init(rfull + 0, 1);
     mbar_init(rfull + 1, 1);
-    mbar_init(acc_full, 1);
+    mbar_init(acc_full, 2);  // one commit from each issuing warp
     mbar_init(dg_ready, 128);
     fence_barrier_init();
     mbar_expect_tx(rfull + 0, r_bytes);
@@ -459,8 +479,8 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
   tc_fence_after();
   cluster.sync();
 
-  if (warp == 1) {
-    // ===================== MMA issuer =====================
+  if (warp < 2) {
+    // ===================== MMA issuers: warp 1 -> M-tiles 0, 2, ...; warp 0 -> tiles 1, 3 =====================
     constexpr uint32_t idesc = instr_desc(kFmtBF16, 0, 0, 128, NPAD);
     const uint32_t dg0 = __shfl_sync(0xffffffffu, smem_u32(dgs), 0);
     const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -468,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
     for (int step = 0; step + 1 < T; step++) {
       mbar_wait(dg_ready, step & 1);
       tc_fence_after();
-      for (int m = 0; m < MT; m++) {
+      for (int m = 1 - warp; m < MT; m += 2) {
 #pragma unroll
         for (int kk = 0; kk < 8; kk++) {
           const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * 2048 + (kk & 3) * 32) >> 4);
@@ -664,7 +684,9 @@ cudaError_t launch_cluster(K kernel, const RecArgs &a, size_t smem, cudaStream_t
   return cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
-size_t fwd_smem_bytes(int H) { return 1024 + (size_t)(H / 64) * (2 * 2048) + 64; }
+// >= 116 KB so that two CTAs never share an SM (each owns 256+ TMEM columns and an issue slot)
+constexpr size_t kSmemFloor = 116 * 1024;
+size_t fwd_smem_bytes(int H) { return std::max(kSmemFloor, 1024 + (size_t)(H / 64) * (2 * 2048) + 64); }
 
 template <int MODE>
 cudaError_t launch_fwd(const RecArgs &a, cudaStream_t stream) {
@@ -683,7 +705,9 @@ cudaError_t launch_fwd(const RecArgs &a, cudaStream_t stream) {
   }
 }
 
-size_t bwd_smem_bytes(int H, int BC) { return 1024 + 4096 + (size_t)2 * (H / UT) * 32 * BC * 4 + 64; }
+size_t bwd_smem_bytes(int H, int BC) {
+  return std::max(kSmemFloor, 1024 + 4096 + (size_t)2 * (H / UT) * 32 * BC * 4 + 64);
+}
 
 template <int MODE>
 cudaError_t launch_bwd(const RecArgs &a, cudaStream_t stream) {

@@ -51,6 +51,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   } while (!done);
 }
 
+// Busy-polling wait (test_wait never suspends the thread): for the latency-critical
+// per-time-step handoffs of the recurrent kernels, where a warp that slept in try_wait was
+// measured to resume ~250 cycles after the phase completed.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
 // ---- TMA ----------------------------------------------------------------------
 // 2-D tiled load: coordinates (c0 = innermost, c1), completion in bytes on `bar`.
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1,
