@@ -26,7 +26,8 @@ struct b200rnnPlan_st {
   bool geometry_ready;
   int launches;
   // reserve layout (floats), per layer
-  std::vector<size_t> r_gates[2], r_cell[2], r_y;
+  std::vector<size_t> r_gates[2], r_cell[2], r_y, r_bias;
+  bool tc_bwd_used;  // the last BackwardData left fused bias gradients in the reserve
   size_t reserve_floats;
   // workspace layout (floats)
   size_t w_colsum, w_splitk, w_pp[2], w_gates[2], workspace_floats;
@@ -186,6 +187,8 @@ b200rnnStatus_t b200rnnCreatePlan(b200rnnPlan_t *plan, b200rnnMode_t mode, int b
     p->r_cell[d].assign(p->layers, 0);
   }
   p->r_y.assign(p->layers, 0);
+  p->r_bias.assign(p->layers, 0);
+  p->tc_bwd_used = false;
   for (int l = 0; l < p->layers; l++) {
     for (int d = 0; d < p->dirs; d++) {
       p->r_gates[d][l] = r;
@@ -197,6 +200,8 @@ b200rnnStatus_t b200rnnCreatePlan(b200rnnPlan_t *plan, b200rnnMode_t mode, int b
       p->r_y[l] = r;
       r = align_up(r + TB * p->HO, 64);
     }
+    p->r_bias[l] = r;  // [chunks of 4 utterances][dirs][2][GH]
+    r = align_up(r + (size_t)((p->B + 3) / 4) * p->dirs * 2 * p->GH, 64);
   }
   p->reserve_floats = r;
   // workspace
@@ -371,9 +376,12 @@ b200rnnStatus_t b200rnnBackwardData(b200rnnPlan_t p, int T, const float *y, cons
       Timed tm(p, 1, stream);
       if (p->tcNC && !getenv("B200RNN_TC_NO_BWD")) {
         a.NC = p->tcNC; a.U = 32; a.BC = p->tcBC;
+        a.bias_partial = rs + p->r_bias[l];
         CK(rec_tc_backward(a, stream));
+        p->tc_bwd_used = true;
       } else {
         CK(rec_fp32_backward(a, stream));
+        p->tc_bwd_used = false;
       }
     }
     p->launches++;
@@ -445,7 +453,16 @@ b200rnnStatus_t b200rnnBackwardWeights(b200rnnPlan_t p, int T, const float *x, c
           CK(gemm_any(p->math, r, stream, &p->launches));
         }
       }
-      // biases
+      // biases: the tensor backward kernel already summed the gate gradients (per batch chunk)
+      if (p->tc_bwd_used) {
+        if (d == 0) {
+          const PseudoLayer &q1 = p->pl[l * p->dirs + (p->dirs - 1)];
+          CK(rec_tc_bias_finalize(rs + p->r_bias[l], (B + p->tcBC - 1) / p->tcBC, p->dirs, GH, dw + q.b_in,
+                                  dw + q.b_rec, dw + q1.b_in, dw + q1.b_rec, stream));
+          p->launches++;
+        }
+        continue;
+      }
       float *part = ws + p->w_colsum;
       CK(column_sums(dg, TB, GH, GH, 1.f, dw + q.b_in, 1, part, p->colsum_floats, stream, &p->launches));
       if (p->mode == 3) {

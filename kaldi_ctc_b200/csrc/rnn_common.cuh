@@ -71,6 +71,8 @@ struct RecArgs {
   const float *dy;        // bwd only
   int save;               // fwd: 1 = keep activations/cell for backward
   long long *dbg;         // optional: per-phase cycle counters of cluster 0 / CTA 0 (tuning aid)
+  float *bias_partial;    // bwd (tensor kernels): [chunk][dir][side 0 = input, 1 = recurrent][G*H] sums of the
+                          // gate gradients over time and the chunk's utterances (the bias gradients)
 };
 // smem bytes for a given geometry (0 = does not fit the fp32 persistent kernels)
 size_t rec_fp32_smem_bytes(int mode, int H, int NC, bool backward);
@@ -86,5 +88,8 @@ bool rec_tc_supported(int mode, int H);
 int rec_tc_pick_chunk(int H, int B, int dirs);
 cudaError_t rec_tc_forward(const RecArgs &a, cudaStream_t stream);  // a.NC = H/32, a.BC in {4,8,16}
 cudaError_t rec_tc_backward(const RecArgs &a, cudaStream_t stream);
+// dw[b_in[d] + n] += sum_chunk partial[chunk][d][0][n];  dw[b_rec[d] + n] += sum_chunk partial[chunk][d][1][n]
+cudaError_t rec_tc_bias_finalize(const float *partial, int nchunks, int dirs, int GH, float *db_in0, float *db_rec0,
+                                 float *db_in1, float *db_rec1, cudaStream_t stream);
 
 }  // namespace b200

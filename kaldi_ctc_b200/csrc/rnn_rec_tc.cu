@@ -509,6 +509,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
     float carry[NJ];  // LSTM: dc carried to the previous step; GRU: dh * z
 #pragma unroll
     for (int j = 0; j < NJ; j++) carry[j] = 0.f;
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f}, bsq = 0.f;  // bias gradients: sums over time and my utterances
 
     // operands of the step, prefetched one step ahead
     float pdy[NJ], pg[NJ][G], pc[NJ], pcp[NJ];
@@ -603,6 +604,8 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
           dq[j] = 0.f;
           carry[j] = 0.f;
         }
+        bsum[0] += dgv[j][0]; bsum[1] += dgv[j][1]; bsum[2] += dgv[j][2]; bsum[3] += dgv[j][3];
+        bsq += dq[j];
       }
       if (step + 1 < T) {
         // ---- recurrent-side gradients -> BF16 B tile [utterance row][gate row r = 4*ul + g]
@@ -650,6 +653,24 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
         tc_fence_before();
       }
     }
+    // ---- bias gradients of this chunk: add the four utterance slots, slot 0 writes
+    if (a.bias_partial) {
+#pragma unroll
+      for (int g = 0; g < 4; g++) {
+        bsum[g] += __shfl_xor_sync(0xffffffffu, bsum[g], 1);
+        bsum[g] += __shfl_xor_sync(0xffffffffu, bsum[g], 2);
+      }
+      bsq += __shfl_xor_sync(0xffffffffu, bsq, 1);
+      bsq += __shfl_xor_sync(0xffffffffu, bsq, 2);
+      if (s == 0) {
+        float *bp = a.bias_partial + (size_t)(chunk * a.dirs + dir) * 2 * GH;
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+          bp[(size_t)g * H + unit] = bsum[g];                                        // input side
+          bp[GH + (size_t)g * H + unit] = (MODE == 3 && g == 2) ? bsq : bsum[g];    // recurrent side
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -658,6 +679,19 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+}
+
+__global__ void bias_finalize_kernel(const float *partial, int nchunks, int dirs, int GH, float *o00, float *o01,
+                                     float *o10, float *o11) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= GH) return;
+  for (int d = 0; d < dirs; d++)
+    for (int side = 0; side < 2; side++) {
+      float sum = 0.f;
+      for (int c = 0; c < nchunks; c++) sum += partial[((size_t)(c * dirs + d) * 2 + side) * GH + n];
+      float *o = d == 0 ? (side == 0 ? o00 : o01) : (side == 0 ? o10 : o11);
+      o[n] += sum;
+    }
 }
 
 template <typename K>
@@ -744,6 +778,12 @@ cudaError_t rec_tc_forward(const RecArgs &a, cudaStream_t stream) {
     case 2: return launch_fwd<2>(a, stream);
     default: return launch_fwd<3>(a, stream);
   }
+}
+
+cudaError_t rec_tc_bias_finalize(const float *partial, int nchunks, int dirs, int GH, float *db_in0, float *db_rec0,
+                                 float *db_in1, float *db_rec1, cudaStream_t stream) {
+  bias_finalize_kernel<<<(GH + 255) / 256, 256, 0, stream>>>(partial, nchunks, dirs, GH, db_in0, db_rec0, db_in1, db_rec1);
+  return cudaGetLastError();
 }
 
 cudaError_t rec_tc_backward(const RecArgs &a, cudaStream_t stream) {
