@@ -31,6 +31,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -174,14 +175,14 @@ ctc_rowstats_gather_kernel(CtcDev d) {
   if ((A & 3) == 0) {
     const float4 *a4 = reinterpret_cast<const float4 *>(a);
     const int n4 = A >> 2;
-    for (int k = lane; k < n4; k += 128) {
-      float4 v[4];
+    for (int k = lane; k < n4; k += 256) {
+      float4 v[8];  // 8 x 16 B per lane in flight
 #pragma unroll
-      for (int u = 0; u < 4; u++)
+      for (int u = 0; u < 8; u++)
         v[u] = (k + 32 * u < n4) ? __ldg(a4 + k + 32 * u)
                                  : make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < 8; u++) {
         float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
         if (mx > m) {
           s *= exp2f((m - mx) * kLog2e);
@@ -207,12 +208,25 @@ ctc_rowstats_gather_kernel(CtcDev d) {
   const float l2 = M * kLog2e + log2f(S);
   if (lane == 0) d.lse2[row] = l2;
 
-  // gather: E[t][0] = blank, E[t][1+i] = label i  (base-2 log-probabilities)
+  // gather: E[t][0] = blank, E[t][1+i] = label i  (base-2 log-probabilities).  The row was just
+  // streamed, so these are L1/L2 hits; four independent gathers per lane in flight.
   float *e = d.E + um.e_off + (long long)t * um.pitch;
   const int *lab = d.labels + um.lab_off;
-  for (int u = lane; u <= um.L; u += 32) {
-    const int k = u == 0 ? d.blank : __ldg(lab + u - 1);
-    e[u] = __ldg(a + k) * kLog2e - l2;
+  for (int u0 = lane; u0 <= um.L; u0 += 128) {
+    int kk[4];
+    float vv[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int u = u0 + 32 * i;
+      kk[i] = u <= um.L ? (u == 0 ? d.blank : __ldg(lab + u - 1)) : d.blank;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) vv[i] = __ldg(a + kk[i]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int u = u0 + 32 * i;
+      if (u <= um.L) e[u] = vv[i] * kLog2e - l2;
+    }
   }
 }
 
@@ -442,18 +456,34 @@ __global__ void __launch_bounds__(kK3Warps * 32) ctc_grad_kernel(CtcDev d, int s
   const float *oa = d.offA + um.off_off + (long long)(t / kRenorm) * nthr;
   const float *ob = d.offB + um.off_off + (long long)((um.T - 1 - t) / kRenorm) * nthr;
   const double lp2 = d.logp2[b];
-  float *sm = gsm + wi * smem_pitch;
-  float z = 0.f;
-  for (int s = lane; s < S; s += 32) {
-    const float ee = (s & 1) ? e[1 + (s >> 1)] : e[0];
-    const float cab = oa[(s >> 1) / P] + ob[(L - ((s + 1) >> 1)) / P];  // exact: integers
-    const float D = (float)((double)cab - lp2);
-    const float v = exp2f(fminf(fmaxf((al[s] + be[s] - ee) + D, -200.f), 100.f));
-    sm[s] = v;
-    z += v;
+  float *sm = gsm + wi * smem_pitch;  // gamma of the LABEL states only: sm[i] = gamma(2i+1)
+  float z = 0.f, zblank = 0.f;
+  // four independent states per lane in flight (the loads dominate this loop)
+  for (int s0 = lane; s0 < S; s0 += 128) {
+    float av[4], bv[4], ev[4], cv[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int s = s0 + 32 * u;
+      const bool ok = s < S;
+      av[u] = ok ? al[s] : kNeg;
+      bv[u] = ok ? be[s] : 0.f;
+      ev[u] = ok ? ((s & 1) ? e[1 + (s >> 1)] : e[0]) : 0.f;
+      cv[u] = ok ? oa[(s >> 1) / P] + ob[(L - ((s + 1) >> 1)) / P] : 0.f;  // exact: integers
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int s = s0 + 32 * u;
+      const float D = (float)((double)cv[u] - lp2);
+      const float v = exp2f(fminf(fmaxf((av[u] + bv[u] - ev[u]) + D, -200.f), 100.f));
+      if (s < S) {
+        z += v;
+        if (s & 1) sm[s >> 1] = v;
+        else zblank += v;
+      }
+    }
   }
   const float Z = warp_sum(z);
-  const float zb = warp_sum((lane & 1) ? 0.f : z);  // even states are blanks
+  const float zb = warp_sum(zblank);  // even states are blanks
   const float invZ = Z > 0.f ? 1.0f / Z : 0.f;
 
   // y = softmax(row), streamed
@@ -461,13 +491,13 @@ __global__ void __launch_bounds__(kK3Warps * 32) ctc_grad_kernel(CtcDev d, int s
     const float4 *a4 = reinterpret_cast<const float4 *>(a);
     float4 *g4 = reinterpret_cast<float4 *>(g);
     const int n4 = A >> 2;
-    for (int k = lane; k < n4; k += 128) {
-      float4 v[4];
+    for (int k = lane; k < n4; k += 256) {
+      float4 v[8];
 #pragma unroll
-      for (int u = 0; u < 4; u++)
+      for (int u = 0; u < 8; u++)
         if (k + 32 * u < n4) v[u] = __ldg(a4 + k + 32 * u);
 #pragma unroll
-      for (int u = 0; u < 4; u++)
+      for (int u = 0; u < 8; u++)
         if (k + 32 * u < n4) {
           float4 y;
           y.x = gs * exp2f(v[u].x * kLog2e - l2);
@@ -480,17 +510,32 @@ __global__ void __launch_bounds__(kK3Warps * 32) ctc_grad_kernel(CtcDev d, int s
   } else {
     for (int k = lane; k < A; k += 32) g[k] = gs * exp2f(__ldg(a + k) * kLog2e - l2);
   }
-  __syncwarp();  // orders the row stores above before the per-label overwrites below
-
-  if (lane == 0) g[d.blank] = gs * (exp2f(__ldg(a + d.blank) * kLog2e - l2) - zb * invZ);
+  // per-label posterior mass from shared memory only (fixed summation order => deterministic)
+  float *corr = sm + (smem_pitch >> 1);
   const int *ul = d.uniq_lab + um.csr_off;
   const int *us = d.uniq_start + um.csr_off + b;  // nuniq+1 entries per utterance
   const int *pos = d.pos + um.lab_off;
   for (int j = lane; j < um.nuniq; j += 32) {
-    const int kk = ul[j];
     float acc = 0.f;
-    for (int q = us[j]; q < us[j + 1]; q++) acc += sm[2 * pos[q] + 1];
-    g[kk] = gs * (exp2f(__ldg(a + kk) * kLog2e - l2) - acc * invZ);
+    for (int q = us[j]; q < us[j + 1]; q++) acc += sm[pos[q]];
+    corr[j] = acc * invZ;
+  }
+  __syncwarp();  // orders the row stores above (and corr[]) before the per-label overwrites below
+
+  if (lane == 0) g[d.blank] = gs * (exp2f(__ldg(a + d.blank) * kLog2e - l2) - zb * invZ);
+  // overwrite the entries of the labels that occur: independent gathers (L2 hits), four in flight
+  for (int j0 = lane; j0 < um.nuniq; j0 += 128) {
+    int kk[4];
+    float vv[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) kk[i] = (j0 + 32 * i < um.nuniq) ? __ldg(ul + j0 + 32 * i) : d.blank;
+#pragma unroll
+    for (int i = 0; i < 4; i++) vv[i] = __ldg(a + kk[i]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int j = j0 + 32 * i;
+      if (j < um.nuniq) g[kk[i]] = gs * (exp2f(vv[i] * kLog2e - l2) - corr[j]);
+    }
   }
 }
 
@@ -592,9 +637,13 @@ bool ensure_pinned(Staging &s, size_t bytes, size_t ncosts) {
 template <int P>
 cudaError_t launch_k2(const CtcDev &dev, int B, int NT, int F, cudaStream_t stream) {
   const size_t smem = 2048 + sizeof(float) * 2 * kStages * kStageFloats;
-  cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_kernel<P>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_kernel<P>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
   ctc_alpha_beta_kernel<P><<<B, 2 * NT, smem, stream>>>(dev, F);
   return cudaGetLastError();
 }
@@ -615,13 +664,19 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   std::lock_guard<std::mutex> lock(g_stage.mu);
   if (!ensure_pinned(g_stage, p.header_bytes, (size_t)B)) return CTC_STATUS_MEMOPS_FAILED;
   unsigned char *h = g_stage.pinned;
-  memset(h, 0, p.header_bytes);
   UttMeta *hm = reinterpret_cast<UttMeta *>(h + p.off_meta);
   int *hl = reinterpret_cast<int *>(h + p.off_labels);
   int *hul = reinterpret_cast<int *>(h + p.off_uniq_lab);
   int *hus = reinterpret_cast<int *>(h + p.off_uniq_start);
   int *hpos = reinterpret_cast<int *>(h + p.off_pos);
-  std::vector<int> order;
+  // label -> states CSR in O(L) per utterance: groups in order of first appearance, positions
+  // ascending inside a group (a fixed summation order => deterministic gradients)
+  static thread_local std::vector<int> stamp, slot, cnt;
+  if ((int)stamp.size() < A) {
+    stamp.assign(A, -1);
+    slot.assign(A, 0);
+  }
+  static thread_local int epoch = 0;
   for (int b = 0; b < B; b++) {
     UttMeta &m = p.meta[b];
     const int *lab = flat_labels + m.lab_off;
@@ -632,21 +687,28 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
       hl[m.lab_off + i] = lab[i];
     }
     m.feasible = (m.L + repeats <= m.T) ? 1 : 0;
-    // label -> positions CSR (positions ascending inside a label: fixed summation order)
-    order.resize(m.L);
-    for (int i = 0; i < m.L; i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return lab[x] < lab[y]; });
+    ++epoch;
     int nu = 0;
     int *us = hus + m.csr_off + b;
-    for (int q = 0; q < m.L; q++) {
-      hpos[m.lab_off + q] = order[q];
-      if (q == 0 || lab[order[q]] != lab[order[q - 1]]) {
-        hul[m.csr_off + nu] = lab[order[q]];
-        us[nu] = q;
+    cnt.assign(m.L + 1, 0);
+    for (int i = 0; i < m.L; i++) {
+      const int k = lab[i];
+      if (stamp[k] != epoch) {
+        stamp[k] = epoch;
+        slot[k] = nu;
+        hul[m.csr_off + nu] = k;
         nu++;
       }
+      cnt[slot[k]]++;
+    }
+    int run_ = 0;
+    for (int j = 0; j < nu; j++) {
+      us[j] = run_;
+      run_ += cnt[j];
+      cnt[j] = us[j];  // becomes the write cursor of group j
     }
     us[nu] = m.L;
+    for (int i = 0; i < m.L; i++) hpos[m.lab_off + cnt[slot[lab[i]]]++] = i;
     m.nuniq = nu;
     hm[b] = m;
   }
@@ -685,7 +747,15 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   dev.P = P;
   const long long rows = (long long)p.Tmax * B;
   const unsigned g1 = (unsigned)((rows + kK1Warps - 1) / kK1Warps);
+  // tuning aid: B200CTC_PROFILE=1 prints the duration of each kernel of the call (CUDA events)
+  const bool prof = getenv("B200CTC_PROFILE") != nullptr;
+  cudaEvent_t ev[4];
+  if (prof) {
+    for (int i = 0; i < 4; i++) cudaEventCreate(&ev[i]);
+    cudaEventRecord(ev[0], stream);
+  }
   ctc_rowstats_gather_kernel<<<g1, kK1Warps * 32, 0, stream>>>(dev);
+  if (prof) cudaEventRecord(ev[1], stream);
   if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
 
   const int NT = (int)align_up((size_t)(npairs + P - 1) / P, 32);
@@ -694,16 +764,32 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
                    : P == 2 ? launch_k2<2>(dev, B, NT, F, stream)
                             : launch_k2<4>(dev, B, NT, F, stream);
   if (ce != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
+  if (prof) cudaEventRecord(ev[2], stream);
 
   if (grad) {
     const int smem_pitch = 2 * p.pitch_max;
     const size_t smem3 = sizeof(float) * (size_t)kK3Warps * smem_pitch;
-    if (cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem3) != cudaSuccess)
-      return CTC_STATUS_EXECUTION_FAILED;
+    static size_t smem3_set = 0;
+    if (smem3 > smem3_set) {
+      if (cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem3) != cudaSuccess)
+        return CTC_STATUS_EXECUTION_FAILED;
+      smem3_set = smem3;
+    }
     const unsigned g3 = (unsigned)((rows + kK3Warps - 1) / kK3Warps);
     ctc_grad_kernel<<<g3, kK3Warps * 32, smem3, stream>>>(dev, smem_pitch);
     if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
+  }
+  if (prof) {
+    cudaEventRecord(ev[3], stream);
+    cudaEventSynchronize(ev[3]);
+    float t1 = 0, t2 = 0, t3 = 0;
+    cudaEventElapsedTime(&t1, ev[0], ev[1]);
+    cudaEventElapsedTime(&t2, ev[1], ev[2]);
+    cudaEventElapsedTime(&t3, ev[2], ev[3]);
+    fprintf(stderr, "[b200ctc] B=%d A=%d Tmax=%d maxL=%d P=%d F=%d: rowstats %.3f ms, alpha_beta %.3f ms, grad %.3f ms\n",
+            B, A, p.Tmax, p.maxL, P, F, t1, t2, t3);
+    for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]);
   }
   if (costs_dev &&
       cudaMemcpyAsync(costs_dev, dev.costs, sizeof(float) * B, cudaMemcpyDeviceToDevice, stream) !=
