@@ -69,6 +69,7 @@ struct CtcDev {
   const float *act;
   float *grad;
   int A, B, Tmax, blank;
+  int b_lo, nb;           // utterance range [b_lo, b_lo+nb) this launch works on
   float grad_scale;
   const UttMeta *meta;
   const int *labels;      // flat labels
@@ -163,9 +164,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __global__ void __launch_bounds__(kK1Warps * 32)
 ctc_rowstats_gather_kernel(CtcDev d) {
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * kK1Warps + (threadIdx.x >> 5);
-  if (row >= (long long)d.Tmax * d.B) return;
-  const int t = (int)(row / d.B), b = (int)(row - (long long)t * d.B);
+  const long long lrow = (long long)blockIdx.x * kK1Warps + (threadIdx.x >> 5);
+  if (lrow >= (long long)d.Tmax * d.nb) return;
+  const int t = (int)(lrow / d.nb), b = d.b_lo + (int)(lrow - (long long)t * d.nb);
+  const long long row = (long long)t * d.B + b;
   const UttMeta um = d.meta[b];
   if (t >= um.T || !um.feasible) return;
   const int A = d.A;
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int f
   float *fin = reinterpret_cast<float *>(smem_raw + 64 + 1024);          // [2][4]
   float *stages = reinterpret_cast<float *>(smem_raw + 2048);            // [2][kStages][kStageFloats]
 
-  const int b = blockIdx.x;
+  const int b = d.b_lo + blockIdx.x;
   const UttMeta um = d.meta[b];
   if (!um.feasible) return;
   const int NT = blockDim.x >> 1;
@@ -425,9 +427,10 @@ __global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int f
 __global__ void __launch_bounds__(kK3Warps * 32) ctc_grad_kernel(CtcDev d, int smem_pitch) {
   extern __shared__ __align__(16) float gsm[];
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  const long long row = (long long)blockIdx.x * kK3Warps + wi;
-  if (row >= (long long)d.Tmax * d.B) return;
-  const int t = (int)(row / d.B), b = (int)(row - (long long)t * d.B);
+  const long long lrow = (long long)blockIdx.x * kK3Warps + wi;
+  if (lrow >= (long long)d.Tmax * d.nb) return;
+  const int t = (int)(lrow / d.nb), b = d.b_lo + (int)(lrow - (long long)t * d.nb);
+  const long long row = (long long)t * d.B + b;
   const UttMeta um = d.meta[b];
   const int A = d.A;
   float *g = d.grad + row * A;
@@ -510,32 +513,33 @@ __global__ void __launch_bounds__(kK3Warps * 32) ctc_grad_kernel(CtcDev d, int s
   } else {
     for (int k = lane; k < A; k += 32) g[k] = gs * exp2f(__ldg(a + k) * kLog2e - l2);
   }
-  // per-label posterior mass from shared memory only (fixed summation order => deterministic)
-  float *corr = sm + (smem_pitch >> 1);
+  __syncwarp();  // orders the row stores above (and sm[]) before the per-label overwrites below
   const int *ul = d.uniq_lab + um.csr_off;
   const int *us = d.uniq_start + um.csr_off + b;  // nuniq+1 entries per utterance
   const int *pos = d.pos + um.lab_off;
-  for (int j = lane; j < um.nuniq; j += 32) {
-    float acc = 0.f;
-    for (int q = us[j]; q < us[j + 1]; q++) acc += sm[pos[q]];
-    corr[j] = acc * invZ;
-  }
-  __syncwarp();  // orders the row stores above (and corr[]) before the per-label overwrites below
 
   if (lane == 0) g[d.blank] = gs * (exp2f(__ldg(a + d.blank) * kLog2e - l2) - zb * invZ);
-  // overwrite the entries of the labels that occur: independent gathers (L2 hits), four in flight
+  // overwrite the entries of the labels that occur.  Per-label posterior mass from shared memory in a
+  // fixed order (deterministic); the activation gathers are L2 hits, four independent ones in flight.
   for (int j0 = lane; j0 < um.nuniq; j0 += 128) {
     int kk[4];
-    float vv[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) kk[i] = (j0 + 32 * i < um.nuniq) ? __ldg(ul + j0 + 32 * i) : d.blank;
-#pragma unroll
-    for (int i = 0; i < 4; i++) vv[i] = __ldg(a + kk[i]);
+    float vv[4], mass[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const int j = j0 + 32 * i;
-      if (j < um.nuniq) g[kk[i]] = gs * (exp2f(vv[i] * kLog2e - l2) - corr[j]);
+      kk[i] = d.blank;
+      mass[i] = 0.f;
+      if (j < um.nuniq) {
+        kk[i] = __ldg(ul + j);
+        const int q1 = __ldg(us + j + 1);
+        for (int q = __ldg(us + j); q < q1; q++) mass[i] += sm[__ldg(pos + q)];
+      }
     }
+#pragma unroll
+    for (int i = 0; i < 4; i++) vv[i] = __ldg(a + kk[i]);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (j0 + 32 * i < um.nuniq) g[kk[i]] = gs * (exp2f(vv[i] * kLog2e - l2) - mass[i] * invZ);
   }
 }
 
@@ -644,7 +648,7 @@ cudaError_t launch_k2(const CtcDev &dev, int B, int NT, int F, cudaStream_t stre
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  ctc_alpha_beta_kernel<P><<<B, 2 * NT, smem, stream>>>(dev, F);
+  ctc_alpha_beta_kernel<P><<<dev.nb, 2 * NT, smem, stream>>>(dev, F);
   return cudaGetLastError();
 }
 
@@ -745,30 +749,13 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   const int npairs = p.maxL + 1;
   const int P = npairs <= 512 ? 1 : (npairs <= 1024 ? 2 : 4);
   dev.P = P;
-  const long long rows = (long long)p.Tmax * B;
-  const unsigned g1 = (unsigned)((rows + kK1Warps - 1) / kK1Warps);
-  // tuning aid: B200CTC_PROFILE=1 prints the duration of each kernel of the call (CUDA events)
-  const bool prof = getenv("B200CTC_PROFILE") != nullptr;
-  cudaEvent_t ev[4];
-  if (prof) {
-    for (int i = 0; i < 4; i++) cudaEventCreate(&ev[i]);
-    cudaEventRecord(ev[0], stream);
-  }
-  ctc_rowstats_gather_kernel<<<g1, kK1Warps * 32, 0, stream>>>(dev);
-  if (prof) cudaEventRecord(ev[1], stream);
-  if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
-
+  // Launch K1 -> K2 -> K3 per utterance group.  With two groups on two streams the latency-bound
+  // alpha/beta recursion of one group runs under the bandwidth-bound row kernels of the other.
   const int NT = (int)align_up((size_t)(npairs + P - 1) / P, 32);
   const int F = std::max(1, std::min(32, kStageFloats / p.pitch_max));
-  cudaError_t ce = P == 1   ? launch_k2<1>(dev, B, NT, F, stream)
-                   : P == 2 ? launch_k2<2>(dev, B, NT, F, stream)
-                            : launch_k2<4>(dev, B, NT, F, stream);
-  if (ce != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
-  if (prof) cudaEventRecord(ev[2], stream);
-
+  const int smem_pitch = p.pitch_max;  // gammas of the label states of one row
+  const size_t smem3 = sizeof(float) * (size_t)kK3Warps * smem_pitch;
   if (grad) {
-    const int smem_pitch = 2 * p.pitch_max;
-    const size_t smem3 = sizeof(float) * (size_t)kK3Warps * smem_pitch;
     static size_t smem3_set = 0;
     if (smem3 > smem3_set) {
       if (cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -776,9 +763,52 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
         return CTC_STATUS_EXECUTION_FAILED;
       smem3_set = smem3;
     }
-    const unsigned g3 = (unsigned)((rows + kK3Warps - 1) / kK3Warps);
-    ctc_grad_kernel<<<g3, kK3Warps * 32, smem3, stream>>>(dev, smem_pitch);
+  }
+  // tuning aid: B200CTC_PROFILE=1 serialises the groups and prints the duration of each kernel
+  const bool prof = getenv("B200CTC_PROFILE") != nullptr;
+  // (only worth it when the row kernels are long: a slab of >= 256 MB)
+  const bool big = (size_t)p.Tmax * B * A >= ((size_t)64 << 20);
+  const int ngroups = (B >= 16 && big && !prof && !getenv("B200CTC_ONE_STREAM")) ? 2 : 1;
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (ngroups == 2 && !side) {
+    if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)
+      return CTC_STATUS_EXECUTION_FAILED;
+  }
+  if (ngroups == 2) {
+    cudaEventRecord(ev_fork, stream);  // header copy + prior work of the caller's stream
+    cudaStreamWaitEvent(side, ev_fork, 0);
+  }
+  cudaEvent_t ev[4];
+  if (prof) {
+    for (int i = 0; i < 4; i++) cudaEventCreate(&ev[i]);
+    cudaEventRecord(ev[0], stream);
+  }
+  for (int gi = 0; gi < ngroups; gi++) {
+    cudaStream_t st = gi == 0 ? stream : side;
+    dev.b_lo = gi == 0 ? 0 : B / 2;
+    dev.nb = ngroups == 1 ? B : (gi == 0 ? B / 2 : B - B / 2);
+    const long long rows = (long long)p.Tmax * dev.nb;
+    const unsigned g1 = (unsigned)((rows + kK1Warps - 1) / kK1Warps);
+    ctc_rowstats_gather_kernel<<<g1, kK1Warps * 32, 0, st>>>(dev);
     if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
+    if (prof) cudaEventRecord(ev[1], st);
+    cudaError_t ce = P == 1   ? launch_k2<1>(dev, B, NT, F, st)
+                     : P == 2 ? launch_k2<2>(dev, B, NT, F, st)
+                              : launch_k2<4>(dev, B, NT, F, st);
+    if (ce != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
+    if (prof) cudaEventRecord(ev[2], st);
+    if (grad) {
+      const unsigned g3 = (unsigned)((rows + kK3Warps - 1) / kK3Warps);
+      ctc_grad_kernel<<<g3, kK3Warps * 32, smem3, st>>>(dev, smem_pitch);
+      if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
+    }
+  }
+  if (ngroups == 2) {
+    cudaEventRecord(ev_join, side);
+    cudaStreamWaitEvent(stream, ev_join, 0);
   }
   if (prof) {
     cudaEventRecord(ev[3], stream);
