@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int f
     const float Eb = e[0];
     float El[P];
 #pragma unroll
-    for (int p = 0; p < P; p++) El[p] = hasX[p] ? e[eidx[p]] : 0.f;
+    for (int p = 0; p < P; p++) El[p] = hasX[p] ? e[eidx[p]] : kNeg;  // kNeg keeps a missing X at "log 0"
 
     float nX[P], nY[P];
 #pragma unroll
@@ -338,14 +338,11 @@ __global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int f
       nY[p] = Eb + lse2_2(Y[p], xp);
       nX[p] = El[p] + lse2_3(X[p], Y[p], skip[p] ? xp : kNeg);
     }
-    float mx = kNeg;
 #pragma unroll
     for (int p = 0; p < P; p++) {
-      Y[p] = hasY[p] ? fmaxf(nY[p], kNeg) : kNeg;
-      X[p] = hasX[p] ? fmaxf(nX[p], kNeg) : kNeg;
-      mx = fmaxf(mx, fmaxf(X[p], Y[p]));
+      Y[p] = nY[p];
+      X[p] = nX[p];
     }
-    live = live || (mx > -1.0e29f);
     // store this frame (relative to c)
     float *o = out + (long long)t * pitch2;
 #pragma unroll
@@ -358,10 +355,16 @@ __global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int f
           *reinterpret_cast<float2 *>(o + 2 * (L - i)) = make_float2(X[p], Y[p]);
       }
     }
-    // end of a frame block: publish the offset the block was stored with, re-centre
-    if ((step % kRenorm) == kRenorm - 1 || step == T - 1) {
+    // end of a frame block: publish the offset the block was stored with, re-centre.  c only changes
+    // here: re-centred if the thread has reachable states, otherwise adopted from the left neighbour.
+    const bool block_end = (step % kRenorm) == kRenorm - 1 || step == T - 1;
+    if (block_end) {
       if (r < nthreads_needed) off_out[(step / kRenorm) * nthreads_needed + r] = c;
-      if (mx > -1.0e29f) {
+      float mx = kNeg;
+#pragma unroll
+      for (int p = 0; p < P; p++) mx = fmaxf(mx, fmaxf(hasX[p] ? X[p] : kNeg, hasY[p] ? Y[p] : kNeg));
+      live = mx > -1.0e29f;
+      if (live) {
         const float sh = floorf(mx);
 #pragma unroll
         for (int p = 0; p < P; p++) {
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int f
       xv = v.x;
       cv = v.y;
     }
-    if (!live) c = cv;                 // nothing reachable here yet: follow the neighbour
+    if (block_end && !live) c = cv;    // nothing reachable here yet: follow the neighbour
     xin = fmaxf(xv + (cv - c), kNeg);  // cv - c is an exact integer
     // stage fully consumed -> refill it with the chunk kStages ahead
     if (r == 0 && (step + 1 == (k + 1) * F) && k + kStages < nchunks) issue(k + kStages);
