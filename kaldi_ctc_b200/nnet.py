@@ -97,7 +97,7 @@ class NnetCtcUpdater:
     """Mirror of kaldi::ctc::NnetCtcUpdater for the BLSTM/BiGRU + CTC topology."""
 
     def __init__(self, spec, blobs, affine_w, affine_b, minibatch, max_frames, device="cuda:0",
-                 math=rnn.MATH_FP32, world=1):
+                 math=rnn.MATH_FP32, world=1, overlap_weights=True):
         self.torch = t = _lib.require_cuda()
         self.device = t.device(device)
         self.spec, self.B, self.math, self.world = spec, minibatch, math, world
@@ -125,6 +125,15 @@ class NnetCtcUpdater:
         self.dact = [t.empty(rows, spec.H * dirs, device=self.device) for _ in range(2)]
         self.costs_dev = t.zeros(minibatch, device=self.device)
         self.costs_host = t.zeros(minibatch, dtype=t.float32).pin_memory()
+        # The weight-gradient GEMMs of layer l (and its clip+update / all-reduce) do not feed layer l-1's
+        # backward: they run on a side stream under the (latency-bound, 80-SM) recurrent kernel of the
+        # next layer.  The step itself runs on a high-priority stream so that the recurrent kernel's
+        # clusters are placed ahead of queued GEMM tiles.
+        lo, hi = t.cuda.Stream.priority_range()
+        self.main_stream = t.cuda.Stream(device=self.device, priority=hi)
+        self.side_stream = t.cuda.Stream(device=self.device, priority=lo) if overlap_weights else None
+        for c in self.rnns:
+            c.side_stream = self.side_stream
         if world > 1:  # data-parallel gradient buffers of the affine layer
             self.gW = t.zeros_like(self.affine.linear_params_)
             self.gb = t.zeros_like(self.affine.bias_params_)
@@ -168,6 +177,8 @@ class NnetCtcUpdater:
         n = len(self.rnns)
         top_in = self.acts[-1][:rows]
         dp = update and self.world > 1
+        for c in self.rnns:  # the all-reduce path keeps its own ordering: no side stream there
+            c.side_stream = None if dp else self.side_stream
         if dp:
             from .parallel import GradientReducer
             red = GradientReducer()
@@ -191,6 +202,8 @@ class NnetCtcUpdater:
                                   want_in_deriv=(l > 0))
         if dp:
             red.finish()
+        if self.side_stream is not None:
+            self.torch.cuda.current_stream(self.device).wait_stream(self.side_stream)
         return d
 
     def ComputeForMinibatch(self, feats_host, T, flat_labels, label_lengths, input_lengths, update=True,
@@ -198,11 +211,16 @@ class NnetCtcUpdater:
         """One training step; returns tot_objf = sum of the per-utterance NLLs (:256).
         feats_host=None keeps the slab already resident in x_dev; host_sync=False leaves the
         step asynchronous (read the objective later with last_objf())."""
-        if feats_host is not None:
-            self.FormatInput(feats_host, T)
-        self.Propagate(T)
-        self.ComputeObjfAndDeriv(T, flat_labels, label_lengths, input_lengths, sync=False)
-        self.Backprop(T, update)
+        t = self.torch
+        cur = t.cuda.current_stream(self.device)
+        self.main_stream.wait_stream(cur)
+        with t.cuda.stream(self.main_stream):
+            if feats_host is not None:
+                self.FormatInput(feats_host, T)
+            self.Propagate(T)
+            self.ComputeObjfAndDeriv(T, flat_labels, label_lengths, input_lengths, sync=False)
+            self.Backprop(T, update)
+        cur.wait_stream(self.main_stream)
         if not host_sync:
             return None
         return self.last_objf()

@@ -137,6 +137,9 @@ class CuDNNRecurrentComponent:
         self.filter_params_ = None
         self.plan = None
         self.launch_counts = {}
+        # optional torch.cuda.Stream: BackwardWeights + Update run there, overlapping whatever the
+        # caller enqueues next (the next component's BackwardData); the caller joins it
+        self.side_stream = None
 
     def Type(self):
         return "CuDNNRecurrentComponent"
@@ -224,14 +227,23 @@ class CuDNNRecurrentComponent:
                    "b200rnnBackwardData")
             self.launch_counts["bwd_data"] = self.plan.last_launches()
             if to_update is not None:
-                self.filter_params_grad_.zero_()
-                _check(lib().b200rnnBackwardWeights(self.plan.h, T, in_value.data_ptr(), out_value.data_ptr(),
-                                                    self.filter_params_grad_.data_ptr(),
-                                                    self.work_space_.data_ptr(), self.reserve_space_.data_ptr(), s),
-                       "b200rnnBackwardWeights")
-                self.launch_counts["bwd_weights"] = self.plan.last_launches()
-                to_update.Update(self.filter_params_grad_, self.clip_gradient_)
+                if self.side_stream is not None:
+                    self.side_stream.wait_stream(torch.cuda.current_stream(self.device))
+                    with torch.cuda.stream(self.side_stream):
+                        self._backward_weights(T, in_value, out_value, to_update)
+                else:
+                    self._backward_weights(T, in_value, out_value, to_update)
         return in_deriv
+
+    def _backward_weights(self, T, in_value, out_value, to_update):
+        torch = self.torch
+        self.filter_params_grad_.zero_()
+        _check(lib().b200rnnBackwardWeights(self.plan.h, T, in_value.data_ptr(), out_value.data_ptr(),
+                                            self.filter_params_grad_.data_ptr(), self.work_space_.data_ptr(),
+                                            self.reserve_space_.data_ptr(), _stream(torch, self.device)),
+               "b200rnnBackwardWeights")
+        self.launch_counts["bwd_weights"] = self.plan.last_launches()
+        to_update.Update(self.filter_params_grad_, self.clip_gradient_)
 
     def Update(self, filter_params_grad, clip):
         torch = self.torch
