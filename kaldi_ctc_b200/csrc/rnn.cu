@@ -30,7 +30,7 @@ struct b200rnnPlan_st {
   bool tc_bwd_used;  // the last BackwardData left fused bias gradients in the reserve
   size_t reserve_floats;
   // workspace layout (floats)
-  size_t w_colsum, w_splitk, w_pp[2], w_gates[2], workspace_floats;
+  size_t w_colsum, w_splitk, w_pp[2], w_gates[2], w_stream, w_cell[2], workspace_floats;
   size_t splitk_floats, colsum_floats;
   // optional event timing: [category] -> recorded (start, stop) pairs
   bool profiling;
@@ -46,8 +46,8 @@ int din_of(const b200rnnPlan_st *p, int layer) { return layer == 0 ? p->D : p->H
 
 b200rnnStatus_t ensure_geometry(b200rnnPlan_st *p) {
   if (p->geometry_ready) return B200RNN_STATUS_SUCCESS;
-  p->NC = rec_fp32_pick_cluster(p->mode, p->H);
-  if (p->NC == 0) return B200RNN_STATUS_NOT_SUPPORTED;
+  p->NC = rec_fp32_pick_cluster(p->mode, p->H);  // 0: no on-chip configuration -> streaming kernels
+  if (getenv("B200RNN_FORCE_STREAM")) p->NC = 0;
   p->BC = 16;
   p->tcNC = p->tcBC = 0;
   if (p->math == 1 && rec_tc_supported(p->mode, p->H)) {
@@ -220,7 +220,11 @@ b200rnnStatus_t b200rnnCreatePlan(b200rnnPlan_t *plan, b200rnnMode_t mode, int b
   for (int d = 0; d < p->dirs; d++) {
     p->w_gates[d] = w;
     w = align_up(w + TB * p->GH, 64);
+    p->w_cell[d] = w;   // inference scratch of the streaming path (cell state through HBM)
+    w = align_up(w + TB * p->H, 64);
   }
+  p->w_stream = w;
+  w = align_up(w + rec_stream_scratch_floats(p->dirs, p->B, p->H), 64);
   p->workspace_floats = w;
   *plan = p;
   return B200RNN_STATUS_SUCCESS;
@@ -290,7 +294,7 @@ b200rnnStatus_t b200rnnForward(b200rnnPlan_t p, int T, const float *x, const flo
     float *out = l == p->layers - 1 ? y : (rs ? rs + p->r_y[l] : ws + p->w_pp[l & 1]);
     RecArgs a = {};
     a.mode = p->mode; a.T = T; a.B = p->B; a.H = p->H; a.dirs = p->dirs;
-    a.NC = p->NC; a.U = p->H / p->NC; a.BC = p->BC;
+    a.NC = p->NC; a.U = p->NC ? p->H / p->NC : 0; a.BC = p->BC;
     a.y = out; a.dy = nullptr; a.save = rs ? 1 : 0;
     for (int d = 0; d < p->dirs; d++) {
       const PseudoLayer &q = p->pl[l * p->dirs + d];
@@ -311,7 +315,7 @@ b200rnnStatus_t b200rnnForward(b200rnnPlan_t p, int T, const float *x, const flo
       a.w_rec[d] = w + q.w_rec;
       a.b_rec[d] = w + q.b_rec;
       a.gates[d] = gates;
-      a.cell[d] = rs ? rs + p->r_cell[d][l] : nullptr;
+      a.cell[d] = rs ? rs + p->r_cell[d][l] : ws + p->w_cell[d];
     }
     {
       Timed tm(p, 0, stream);
@@ -336,8 +340,11 @@ b200rnnStatus_t b200rnnForward(b200rnnPlan_t p, int T, const float *x, const flo
                   (h[13] - h[12]) / n, (h[14] - h[15]) / n + (double)(h[8] + h[9] + h[10] + h[11]) / n);
           fprintf(stderr, "[b200rnn fwd tc] tcgen05.fence::after_thread_sync in the epilogue: %.0f cyc\n", h[16] / n);
         }
-      } else {
+      } else if (p->NC) {
         CK(rec_fp32_forward(a, stream));
+      } else {
+        CK(rec_stream_forward(a, stream));
+        p->launches += T - 1;
       }
     }
     p->launches++;
@@ -363,7 +370,7 @@ b200rnnStatus_t b200rnnBackwardData(b200rnnPlan_t p, int T, const float *y, cons
     float *dxl = l == 0 ? dx : ws + p->w_pp[(l - 1) & 1];
     RecArgs a = {};
     a.mode = p->mode; a.T = T; a.B = p->B; a.H = p->H; a.dirs = p->dirs;
-    a.NC = p->NC; a.U = p->H / p->NC; a.BC = p->BC;
+    a.NC = p->NC; a.U = p->NC ? p->H / p->NC : 0; a.BC = p->BC;
     a.y = const_cast<float *>(yl); a.dy = dyl; a.save = 1;
     for (int d = 0; d < p->dirs; d++) {
       const PseudoLayer &q = p->pl[l * p->dirs + d];
@@ -379,9 +386,13 @@ b200rnnStatus_t b200rnnBackwardData(b200rnnPlan_t p, int T, const float *y, cons
         a.bias_partial = rs + p->r_bias[l];
         CK(rec_tc_backward(a, stream));
         p->tc_bwd_used = true;
-      } else {
+      } else if (p->NC) {
         CK(rec_fp32_backward(a, stream));
         p->tc_bwd_used = false;
+      } else {
+        CK(rec_stream_backward(a, ws + p->w_stream, stream));
+        p->tc_bwd_used = false;
+        p->launches += 2 * T - 2;
       }
     }
     p->launches++;

@@ -92,4 +92,11 @@ cudaError_t rec_tc_backward(const RecArgs &a, cudaStream_t stream);
 cudaError_t rec_tc_bias_finalize(const float *partial, int nchunks, int dirs, int GH, float *db_in0, float *db_rec0,
                                  float *db_in1, float *db_rec1, cudaStream_t stream);
 
+// ------------------------------------------------------------------------
+// general streaming path (rnn_rec_stream.cu): any shape, one launch per time step, fp32
+// ------------------------------------------------------------------------
+size_t rec_stream_scratch_floats(int dirs, int B, int H);
+cudaError_t rec_stream_forward(const RecArgs &a, cudaStream_t stream);   // needs a.cell even when !a.save (LSTM)
+cudaError_t rec_stream_backward(const RecArgs &a, float *scratch, cudaStream_t stream);
+
 }  // namespace b200

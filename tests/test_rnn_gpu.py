@@ -9,7 +9,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN_OK = ["rnn_lstm_bi", "rnn_lstm_uni2", "rnn_gru_bi", "rnn_gru_bi2", "rnn_relu_bi", "rnn_tanh_uni"]
+GOLDEN_OK = ["rnn_lstm_bi", "rnn_lstm_uni2", "rnn_gru_bi", "rnn_gru_bi2", "rnn_relu_bi", "rnn_tanh_uni",
+             "rnn_gru_odd", "rnn_lstm_odd"]   # the odd hidden sizes take the general streaming kernels
 
 
 @pytest.fixture(scope="module")
@@ -159,3 +160,26 @@ def test_clip_row_norm_and_column_sums(T):
     ws = T.empty(1 << 20, dtype=T.uint8, device="cuda")
     rnn.column_sums(T, dt, out, True, ws)
     _assert_close(out.cpu().numpy(), 1.0 + want.astype(np.float64).sum(0), 1e-5, "colsum")
+
+
+@pytest.mark.parametrize("mode,D,H,B,Tn", [(2, 20, 64, 5, 9), (3, 12, 48, 19, 6), (0, 8, 33, 2, 5), (2, 16, 1100, 3, 4)])
+def test_general_streaming_path(T, monkeypatch, mode, D, H, B, Tn):
+    """Shapes the persistent kernels cannot hold on chip (any H, e.g. 33 or 1100) and, forced through
+    B200RNN_FORCE_STREAM, ordinary ones: per-time-step launches, weights streamed from L2."""
+    from kaldi_ctc_b200 import rnn
+    from oracle import pyoracle
+    monkeypatch.setenv("B200RNN_FORCE_STREAM", "1")
+    rng = np.random.default_rng(H + B)
+    n = pyoracle.rnn_param_count(mode, True, 1, D, H)
+    w = (rng.standard_normal(n) * (0.3 / np.sqrt(H))).astype(np.float32)
+    x = rng.standard_normal((Tn * B, D)).astype(np.float32)
+    dy = rng.standard_normal((Tn * B, 2 * H)).astype(np.float32)
+    yr, dxr, dwr = pyoracle.rnn(mode, True, 1, H, x, w, B, dy=dy, dtype=np.float64)
+    y, dx, dw = _run(T, rnn, mode, True, 1, D, H, B, x, w, dy)
+    _assert_close(y, yr, 1e-5, "y")
+    _assert_close(dx, dxr, 1e-4, "dx")
+    _assert_close(dw, dwr, 1e-4, "dw")
+    # inference entry point on the same path
+    c = _component(rnn, mode, True, 1, D, H, 1, Tn, w)
+    y1 = c.Propagate(T.from_numpy(x[:Tn]).cuda()).cpu().numpy()
+    _assert_close(y1, pyoracle.rnn(mode, True, 1, H, x[:Tn], w, 1, dtype=np.float64), 1e-5, "y (B=1)")
