@@ -6,6 +6,7 @@
  *     247-248)  -> caller-owned workspace, any stream, optional no-sync
  *   - deriv->Scale(-1) in NnetCtcUpdater::Backprop (:323) -> grad_scale
  *   - deriv->Sum() NaN check (:232-234) -> *nonfinite flag written by the kernel
+ *   - FindRowMaxId for the accuracy (:270-273), a third read of the slab -> argmax_dev
  * Same data layout and semantics as include/ctc.h.
  */
 #ifndef B200CTC_H_
@@ -24,6 +25,10 @@ typedef struct {
   CUstream stream;    /* stream to enqueue on */
   int no_sync;        /* 1: do not synchronise; costs_host may then be NULL and
                          costs are only available in costs_dev */
+  int *argmax_dev;    /* optional DEVICE [T*minibatch] ints: arg-max symbol of every valid row
+                         (what FindRowMaxId gives NnetCtcUpdater::ComputeTotAccuracy,
+                         ctc-nnet-update.cc:270-273), produced by the pass that already
+                         streams the row; rows past input_lengths get -1.  NULL: skipped. */
 } b200ctcOptions;
 
 /* Same as get_workspace_size. */

@@ -85,6 +85,7 @@ struct CtcDev {
   double *logp2;          // [2*B]: alpha-side and beta-side log2 p(l|x)
   float *costs;           // [B]
   int *flags;             // [0]: non-finite cost seen
+  int *argmax;            // optional [Tmax*B]: arg-max symbol per row (-1 on padded rows)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -169,11 +170,16 @@ ctc_rowstats_gather_kernel(CtcDev d) {
   const int t = (int)(lrow / d.nb), b = d.b_lo + (int)(lrow - (long long)t * d.nb);
   const long long row = (long long)t * d.B + b;
   const UttMeta um = d.meta[b];
-  if (t >= um.T || !um.feasible) return;
+  if (t >= um.T) {
+    if (d.argmax && lane == 0) d.argmax[row] = -1;
+    return;
+  }
+  if (!um.feasible && !d.argmax) return;
   const int A = d.A;
   const float *a = d.act + row * A;
 
   float m = -3.0e38f, s = 0.f;
+  int am = 0;  // index of the running maximum (first occurrence)
   if ((A & 3) == 0) {
     const float4 *a4 = reinterpret_cast<const float4 *>(a);
     const int n4 = A >> 2;
@@ -189,6 +195,8 @@ ctc_rowstats_gather_kernel(CtcDev d) {
         if (mx > m) {
           s *= exp2f((m - mx) * kLog2e);
           m = mx;
+          const int k0 = 4 * (k + 32 * u);
+          am = v[u].x == mx ? k0 : (v[u].y == mx ? k0 + 1 : (v[u].z == mx ? k0 + 2 : k0 + 3));
         }
         s += exp2f((v[u].x - m) * kLog2e) + exp2f((v[u].y - m) * kLog2e) +
              exp2f((v[u].z - m) * kLog2e) + exp2f((v[u].w - m) * kLog2e);
@@ -200,11 +208,19 @@ ctc_rowstats_gather_kernel(CtcDev d) {
       if (v > m) {
         s *= exp2f((m - v) * kLog2e);
         m = v;
+        am = k;
       }
       s += exp2f((v - m) * kLog2e);
     }
   }
   const float M = warp_max(m);
+  if (d.argmax) {  // smallest index among the lanes that hold the row maximum (FindRowMaxId's tie rule)
+    int cand = m == M ? am : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+    if (lane == 0) d.argmax[row] = cand;
+    if (!um.feasible) return;
+  }
   s *= exp2f((m - M) * kLog2e);
   const float S = warp_sum(s);
   const float l2 = M * kLog2e + log2f(S);
@@ -747,6 +763,7 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   dev.logp2 = reinterpret_cast<double *>(w + p.off_logp2);
   dev.costs = reinterpret_cast<float *>(w + p.off_costs);
   dev.flags = reinterpret_cast<int *>(w + p.off_flags);
+  dev.argmax = opt.argmax_dev;
 
   // K2 geometry: P pairs per thread so that one direction fits 512 threads
   const int npairs = p.maxL + 1;
@@ -897,6 +914,7 @@ ctcStatus_t compute_ctc_loss(const float *const activations, float *gradients,
   o.grad_scale = 1.0f;
   o.stream = options.stream;
   o.no_sync = 0;
+  o.argmax_dev = nullptr;
   size_t need = 0;
   ctcStatus_t st = b200ctc_workspace_size(label_lengths, input_lengths, alphabet_size, minibatch, &need);
   if (st != CTC_STATUS_SUCCESS) return st;

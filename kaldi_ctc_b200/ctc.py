@@ -23,7 +23,7 @@ class CtcOptions(ctypes.Structure):  # struct ctcOptions of include/ctc.h
 
 class B200CtcOptions(ctypes.Structure):  # b200ctcOptions of include/b200ctc.h
     _fields_ = [("blank_label", ctypes.c_int), ("grad_scale", ctypes.c_float),
-                ("stream", ctypes.c_void_p), ("no_sync", ctypes.c_int)]
+                ("stream", ctypes.c_void_p), ("no_sync", ctypes.c_int), ("argmax_dev", ctypes.c_void_p)]
 
 
 class CtcError(RuntimeError):
@@ -126,14 +126,14 @@ class CtcLoss:
         return costs, (gradients if want_grad else None)
 
     def compute_extended(self, activations, flat_labels, label_lengths, input_lengths, blank=0,
-                         gradients=None, grad_scale=1.0, costs_dev=None, no_sync=False):
+                         gradients=None, grad_scale=1.0, costs_dev=None, no_sync=False, argmax_dev=None):
         torch = self.torch
         T, B, A = activations.shape
         fl, ll, il = _i32(flat_labels), _i32(label_lengths), _i32(input_lengths)
         ws = self._workspace(workspace_size(ll, il, A))
         costs = None if no_sync else np.zeros(B, dtype=np.float32)
         opt = B200CtcOptions(blank, grad_scale, torch.cuda.current_stream(self.device).cuda_stream,
-                             1 if no_sync else 0)
+                             1 if no_sync else 0, argmax_dev.data_ptr() if argmax_dev is not None else None)
         with torch.cuda.device(self.device):
             st = lib().b200ctc_loss(activations.data_ptr(),
                                     gradients.data_ptr() if gradients is not None else None,

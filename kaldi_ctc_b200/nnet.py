@@ -93,6 +93,40 @@ class _Grab:
         pass
 
 
+def collapse_best_path(best_pdf, blank_id=0):
+    """The 'remove blank, and uniq labels' loop of ComputeTotAccuracy (ctc-nnet-update.cc:290-302),
+    quirk included: frame 0's symbol is always kept, blank or not ("at least one label")."""
+    hyp = [int(best_pdf[0])]
+    for j in range(1, len(best_pdf)):
+        if best_pdf[j] != best_pdf[j - 1] and best_pdf[j] != blank_id:
+            hyp.append(int(best_pdf[j]))
+    return hyp
+
+
+def levenshtein(a, b):
+    """util/edit-distance-inl.h LevenshteinEditDistance: unit costs, two rolling rows."""
+    prev = list(range(len(b) + 1))
+    for i in range(1, len(a) + 1):
+        cur = [i] + [0] * len(b)
+        ai = a[i - 1]
+        for j in range(1, len(b) + 1):
+            cur[j] = min(prev[j - 1] + (ai != b[j - 1]), prev[j] + 1, cur[j - 1] + 1)
+        prev = cur
+    return prev[len(b)]
+
+
+def tot_accuracy(best_pdf_tb, flat_labels, label_lengths, input_lengths, blank_id=0):
+    """best_pdf_tb: [T, B] ints (row t*B+b of the reference's best_pdf_cpu)."""
+    tot_num, err_num, off = 0, 0, 0
+    for m, (L, Tm) in enumerate(zip(label_lengths, input_lengths)):
+        labels = [int(v) for v in flat_labels[off:off + L]]
+        off += L
+        assert blank_id not in labels
+        tot_num += L
+        err_num += levenshtein(labels, collapse_best_path(best_pdf_tb[:Tm, m], blank_id))
+    return float(tot_num - err_num), float(tot_num)
+
+
 class NnetCtcUpdater:
     """Mirror of kaldi::ctc::NnetCtcUpdater for the BLSTM/BiGRU + CTC topology."""
 
@@ -125,6 +159,8 @@ class NnetCtcUpdater:
         self.dact = [t.empty(rows, spec.H * dirs, device=self.device) for _ in range(2)]
         self.costs_dev = t.zeros(minibatch, device=self.device)
         self.costs_host = t.zeros(minibatch, dtype=t.float32).pin_memory()
+        self.best_pdf = None       # [rows] int32, filled by the CTC pass when accuracy is wanted
+        self.best_pdf_host = None
         # The weight-gradient GEMMs of layer l (and its clip+update / all-reduce) do not feed layer l-1's
         # backward: they run on a side stream under the (latency-bound, 80-SM) recurrent kernel of the
         # next layer.  The step itself runs on a high-priority stream so that the recurrent kernel's
@@ -154,14 +190,22 @@ class NnetCtcUpdater:
             h = clip.Propagate(c.Propagate(h, out[:rows]))
         return self.affine.Propagate(h, self.logits[:rows])
 
-    def ComputeObjfAndDeriv(self, T, flat_labels, label_lengths, input_lengths, sync=True):
+    def ComputeObjfAndDeriv(self, T, flat_labels, label_lengths, input_lengths, sync=True, want_best_pdf=False):
+        t = self.torch
         rows = T * self.B
         act = self.logits[:rows].view(T, self.B, self.spec.A)
         grad = self.deriv[:rows].view(T, self.B, self.spec.A)
-        # grad_scale=-1 fuses deriv->Scale(-1) of NnetCtcUpdater::Backprop (:323)
+        if want_best_pdf and self.best_pdf is None:
+            self.best_pdf = t.empty(self.max_frames * self.B, dtype=t.int32, device=self.device)
+            self.best_pdf_host = t.empty(self.max_frames * self.B, dtype=t.int32).pin_memory()
+        # grad_scale=-1 fuses deriv->Scale(-1) of NnetCtcUpdater::Backprop (:323); argmax_dev fuses
+        # output.FindRowMaxId of ComputeTotAccuracy (:270-273) into the pass that reads the rows anyway
         self.ctc.compute_extended(act, flat_labels, label_lengths, input_lengths, blank=0, gradients=grad,
-                                  grad_scale=-1.0, costs_dev=self.costs_dev, no_sync=True)
+                                  grad_scale=-1.0, costs_dev=self.costs_dev, no_sync=True,
+                                  argmax_dev=self.best_pdf if want_best_pdf else None)
         self.costs_host.copy_(self.costs_dev, non_blocking=True)
+        if want_best_pdf:
+            self.best_pdf_host[:rows].copy_(self.best_pdf[:rows], non_blocking=True)
         if sync:
             self.torch.cuda.current_stream(self.device).synchronize()
             return float(self.costs_host.sum())
@@ -206,8 +250,17 @@ class NnetCtcUpdater:
             self.torch.cuda.current_stream(self.device).wait_stream(self.side_stream)
         return d
 
+    def ComputeTotAccuracy(self, T, flat_labels, label_lengths, input_lengths):
+        """NnetCtcUpdater::ComputeTotAccuracy (ctc-nnet-update.cc:261-314) on the best_pdf of the
+        last ComputeObjfAndDeriv(want_best_pdf=True).  Returns (tot_accuracy, tot_weight) =
+        (sum |labels| - sum edit distance, sum |labels|).  The device part (row arg-max) came out of
+        the CTC kernel; the per-utterance collapse + edit distance is host work, as in the reference."""
+        self.torch.cuda.current_stream(self.device).synchronize()
+        best = self.best_pdf_host[:T * self.B].numpy().reshape(T, self.B)
+        return tot_accuracy(best, flat_labels, label_lengths, input_lengths)
+
     def ComputeForMinibatch(self, feats_host, T, flat_labels, label_lengths, input_lengths, update=True,
-                            host_sync=True):
+                            host_sync=True, want_best_pdf=False):
         """One training step; returns tot_objf = sum of the per-utterance NLLs (:256).
         feats_host=None keeps the slab already resident in x_dev; host_sync=False leaves the
         step asynchronous (read the objective later with last_objf())."""
@@ -218,7 +271,8 @@ class NnetCtcUpdater:
             if feats_host is not None:
                 self.FormatInput(feats_host, T)
             self.Propagate(T)
-            self.ComputeObjfAndDeriv(T, flat_labels, label_lengths, input_lengths, sync=False)
+            self.ComputeObjfAndDeriv(T, flat_labels, label_lengths, input_lengths, sync=False,
+                                     want_best_pdf=want_best_pdf)
             self.Backprop(T, update)
         cur.wait_stream(self.main_stream)
         if not host_sync:

@@ -93,3 +93,37 @@ def rnn(mode, bidir, layers, H, x, w, B, dy=None, dtype=np.float32,
             _p(dx), _p(dw), num_threads)
     assert st == 0
     return y, dx, dw
+
+
+def tot_accuracy(output, flat_labels, label_lengths, input_lengths, minibatch, blank_id=0):
+    """NnetCtcUpdater::ComputeTotAccuracy, src/ctc/ctc-nnet-update.cc:261-314, restated.
+
+    output: [T*minibatch, A] network output, row t*minibatch+m (:283).  Returns
+    (tot_accuracy, tot_weight).  FindRowMaxId (:272) = first index of the row maximum
+    (np.argmax has the same tie rule); the collapse loop (:290-302) starts at i=j=1, so
+    frame 0's symbol always survives, blank or not; the edit distance is
+    util/edit-distance-inl.h's unit-cost Levenshtein, here as the full DP table."""
+    output = np.asarray(output)
+    best = output.argmax(axis=1)
+    tot_num = err_num = 0
+    off = 0
+    for m in range(minibatch):
+        L, Tm = int(label_lengths[m]), int(input_lengths[m])
+        ref = [int(v) for v in flat_labels[off:off + L]]
+        off += L
+        tot_num += L
+        hyp = [int(best[i * minibatch + m]) for i in range(Tm)]
+        i = 1
+        for j in range(1, Tm):
+            if hyp[j] != hyp[j - 1] and hyp[j] != blank_id:
+                hyp[i] = hyp[j]
+                i += 1
+        hyp = hyp[:i]
+        d = np.zeros((len(ref) + 1, len(hyp) + 1), dtype=np.int64)
+        d[:, 0] = np.arange(len(ref) + 1)
+        d[0, :] = np.arange(len(hyp) + 1)
+        for a in range(1, len(ref) + 1):
+            for b in range(1, len(hyp) + 1):
+                d[a, b] = min(d[a - 1, b - 1] + (ref[a - 1] != hyp[b - 1]), d[a - 1, b] + 1, d[a, b - 1] + 1)
+        err_num += int(d[len(ref), len(hyp)])
+    return float(tot_num - err_num), float(tot_num)

@@ -149,3 +149,43 @@ def test_deterministic(ctx):
     r2 = _run(ctx, bt.activations, bt.flat_labels, bt.label_lengths, bt.input_lengths)
     np.testing.assert_array_equal(r1[0], r2[0])
     np.testing.assert_array_equal(r1[1], r2[1])
+
+
+def test_fused_row_argmax_matches_find_row_max_id(ctx):
+    """argmax_dev of b200ctc_loss == CuMatrix::FindRowMaxId on the valid rows (first maximum wins),
+    -1 on padded rows; costs/gradients unchanged by asking for it."""
+    torch, ctc, op = ctx
+    from kaldi_ctc_b200 import synth
+    for A, seed in ((46, 1), (131, 2), (8000, 3), (7, 4)):
+        bt = synth.ctc_batch(5, A, 20, 60, 2, 9, seed)
+        act = bt.activations.copy()
+        T, B, _ = act.shape
+        act[3, 1, :] = 0.25            # full tie -> index 0
+        act[4, 2, A - 1] = act[4, 2, 2] = 50.0   # two-way tie -> the lower index
+        a = torch.from_numpy(act).cuda()
+        g0 = torch.empty_like(a)
+        c0 = op.compute_extended(a, bt.flat_labels, bt.label_lengths, bt.input_lengths, gradients=g0)
+        g1 = torch.empty_like(a)
+        am = torch.full((T * B,), -7, dtype=torch.int32, device="cuda")
+        c1 = op.compute_extended(a, bt.flat_labels, bt.label_lengths, bt.input_lengths, gradients=g1,
+                                 argmax_dev=am)
+        torch.cuda.synchronize()
+        assert np.array_equal(c0, c1) and torch.equal(g0, g1)
+        got = am.cpu().numpy().reshape(T, B)
+        want = act.argmax(axis=2)
+        for b, Tb in enumerate(bt.input_lengths):
+            assert np.array_equal(got[:Tb, b], want[:Tb, b])
+            assert np.all(got[Tb:, b] == -1)
+        assert got[3, 1] == 0 and got[4, 2] == 2
+
+
+def test_argmax_written_for_infeasible_utterances_too(ctx):
+    torch, ctc, op = ctx
+    rng = np.random.default_rng(0)
+    act = rng.standard_normal((4, 2, 6)).astype(np.float32)
+    fl, ll, il = np.array([1, 1, 1, 2], dtype=np.int32), np.array([3, 1]), np.array([4, 4])  # utt 0 needs 5 frames
+    a = torch.from_numpy(act).cuda()
+    am = torch.full((8,), -7, dtype=torch.int32, device="cuda")
+    op.compute_extended(a, fl, ll, il, gradients=torch.empty_like(a), argmax_dev=am)
+    torch.cuda.synchronize()
+    assert np.array_equal(am.cpu().numpy().reshape(4, 2), act.argmax(2))

@@ -30,3 +30,20 @@ def test_training_step_matches_oracle(mode, H, B, Tn):
     # a second step runs on the updated model and lowers nothing silently: finite objective
     objf2 = up.ComputeForMinibatch(torch.from_numpy(x).pin_memory(), Tmax, fl, L, T)
     assert np.isfinite(objf2)
+
+
+def test_tot_accuracy_matches_oracle():
+    """ComputeTotAccuracy through the fused arg-max vs the oracle on the product's own logits."""
+    import torch
+    from kaldi_ctc_b200 import nnet, synth
+    from oracle import pyoracle
+    spec = synth.ModelSpec(mode=2, layers=1, D=10, H=32, A=12, learning_rate=0.0, param_stddev=0.5)
+    blobs, aw, ab = synth.model_weights(spec, 4)
+    B, Tn = 6, 40
+    x, fl, L, T = synth.features(B, spec.D, Tn - 15, Tn, 3, 8, spec.A, seed=9)
+    Tmax = int(T.max())
+    up = nnet.NnetCtcUpdater(spec, blobs, aw, ab, B, Tmax)
+    up.ComputeForMinibatch(torch.from_numpy(x).pin_memory(), Tmax, fl, L, T, update=False, want_best_pdf=True)
+    acc, w = up.ComputeTotAccuracy(Tmax, fl, L, T)
+    want = pyoracle.tot_accuracy(up.logits[:Tmax * B].cpu().numpy(), fl, L, T, B)
+    assert (acc, w) == want and w == float(np.sum(L))
