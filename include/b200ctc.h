@@ -57,6 +57,32 @@ size_t b200ctc_algorithmic_bytes(const int *label_lengths,
 /* Number of kernels one b200ctc_loss call launches (for bench.py's count). */
 int b200ctc_launches_per_call(int with_gradients);
 
+/*
+ * Decoding side: everything CtcDecodableAmNnet's constructor does to the
+ * network output after NnetComputation (src/ctc/ctc-decodable-am-nnet.cc:54-86), and
+ * CtcDecodableAmNnetParallel::Compute's variant (:89-108), for `minibatch` utterances at once:
+ *   keep frame t of utterance u  iff  p(blank | t,u) < blank_threshold     (:54-60; all frames when
+ *     blank_threshold >= 1, and all frames of an utterance none of whose frames pass, :62-63)
+ *   log_probs[kept row][k] = prob_scale * (log(max(p[k], floor_value)) - log(priors[k]))   (:72-83)
+ * nnet_output: DEVICE [T_max*minibatch, alphabet_size], row t*minibatch+u (minibatch=1 is the
+ *   reference's per-utterance matrix).  input_is_logits=1: the rows are the affine layer's output and
+ *   the appended SoftmaxComponent (steps/ctc/train.sh:471-476) is folded into the same pass;
+ *   0: the rows are already probabilities.
+ * priors: DEVICE [alphabet_size] raw priors (AmNnet::Priors()) or NULL (Priors().Dim()==0, :76).
+ * floor_value: 1e-10 (constructor, :72) or 1e-20 (Parallel::Compute, :93).
+ * log_probs: DEVICE [sum_u input_lengths[u], alphabet_size]; utterance u's kept rows start at row
+ *   sum_{v<u} input_lengths[v] and number kept[u] (<= input_lengths[u]); the rest is untouched.
+ * kept_dev (DEVICE, may be NULL) / kept_host (HOST, may be NULL; non-NULL synchronises the stream).
+ */
+ctcStatus_t b200ctc_decodable_workspace_size(const int *input_lengths, int alphabet_size,
+                                             int minibatch, size_t *size_bytes);
+ctcStatus_t b200ctc_decodable(const float *nnet_output, int input_is_logits,
+                              const int *input_lengths, int alphabet_size, int minibatch,
+                              const float *priors, float prob_scale, float blank_threshold,
+                              float floor_value, float *log_probs, int *kept_dev,
+                              int *kept_host, void *workspace, size_t workspace_bytes,
+                              CUstream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -194,7 +194,7 @@ class CuDNNRecurrentComponent:
     def SetParams(self, blob):
         self.filter_params_ = self.torch.as_tensor(np.asarray(blob, dtype=np.float32)).to(self.device).clone()
 
-    def Propagate(self, inp, out=None):
+    def Propagate(self, inp, out=None, inference=False):
         torch = self.torch
         if self.mini_batch_ == 0:
             self.InitMiniBatch(1)
@@ -205,7 +205,8 @@ class CuDNNRecurrentComponent:
             self.InitMiniBatch(self.mini_batch_, T)
         if out is None:
             out = torch.empty(inp.shape[0], self.OutputDim(), device=self.device)
-        reserve = None if self.mini_batch_ == 1 else self.reserve_space_.data_ptr()  # :534: B==1 -> inference
+        # :534: B==1 -> cudnnRNNForwardInference (no reserve space)
+        reserve = None if (self.mini_batch_ == 1 or inference) else self.reserve_space_.data_ptr()
         with torch.cuda.device(self.device):
             _check(lib().b200rnnForward(self.plan.h, T, inp.data_ptr(), self.filter_params_.data_ptr(),
                                         out.data_ptr(), self.work_space_.data_ptr(), reserve,

@@ -127,3 +127,23 @@ def tot_accuracy(output, flat_labels, label_lengths, input_lengths, minibatch, b
                 d[a, b] = min(d[a - 1, b - 1] + (ref[a - 1] != hyp[b - 1]), d[a - 1, b] + 1, d[a, b - 1] + 1)
         err_num += int(d[len(ref), len(hyp)])
     return float(tot_num - err_num), float(tot_num)
+
+
+def decodable(nnet_output, prob_scale=1.0, blank_threshold=1.0, priors=None, floor=1e-10, is_logits=True,
+              dtype=np.float64):
+    """CtcDecodableAmNnet's constructor after NnetComputation, src/ctc/ctc-decodable-am-nnet.cc:54-86
+    (floor=1e-20, blank_threshold=1.0 gives CtcDecodableAmNnetParallel::Compute, :89-108), for ONE
+    utterance.  nnet_output: [T, A]; is_logits -> the appended SoftmaxComponent
+    (nnet-component.cc SoftmaxComponent::Propagate = ApplySoftMaxPerRow) is applied first."""
+    p = np.asarray(nnet_output, dtype=dtype)
+    if is_logits:
+        e = np.exp(p - p.max(axis=1, keepdims=True))
+        p = e / e.sum(axis=1, keepdims=True)
+    if blank_threshold < 1.0:                       # :54
+        keep = np.nonzero(p[:, 0] < dtype(blank_threshold))[0]   # :56-59
+        if len(keep) != p.shape[0] and len(keep) != 0:          # :60-68
+            p = p[keep]
+    lp = np.log(np.maximum(p, dtype(floor)))        # :72-73
+    if priors is not None:
+        lp = lp - np.log(np.asarray(priors, dtype=dtype))[None, :]   # :76-81
+    return lp * dtype(prob_scale)                   # :83

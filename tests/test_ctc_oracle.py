@@ -105,3 +105,19 @@ def test_fp32_oracle_drift_at_full_length_is_bounded():
     c32, g32 = pyoracle.ctc(bt.activations, bt.flat_labels, bt.label_lengths, bt.input_lengths, dtype=np.float32)
     np.testing.assert_allclose(c32, c64, rtol=1e-5)
     assert np.abs(g32 - g64).max() < 5e-2  # loose: fp32 ulp at |alpha| ~ 8e3 is 5e-4
+
+
+def test_decodable_oracle_known_answers():
+    """Hand-checked: ctc-decodable-am-nnet.cc:54-86 on a 3-frame, 2-symbol matrix."""
+    from oracle import pyoracle
+    p = np.array([[0.99, 0.01], [0.5, 0.5], [0.0, 1.0]])
+    lp = pyoracle.decodable(p, prob_scale=2.0, blank_threshold=0.98, priors=[0.5, 0.25], is_logits=False)
+    assert lp.shape == (2, 2)                                     # frame 0 skipped
+    np.testing.assert_allclose(lp[0], 2.0 * (np.log(0.5) - np.log([0.5, 0.25])))
+    np.testing.assert_allclose(lp[1], 2.0 * (np.log([1e-10, 1.0]) - np.log([0.5, 0.25])))
+    # nothing passes the threshold -> nothing skipped (:62-63); threshold 1.0 -> no filtering at all
+    assert pyoracle.decodable(p, blank_threshold=-1.0, is_logits=False).shape == (3, 2)
+    assert pyoracle.decodable(p, blank_threshold=1.0, is_logits=False).shape == (3, 2)
+    # logits path = softmax first
+    x = np.log(np.array([[0.2, 0.8], [0.6, 0.4]]))
+    np.testing.assert_allclose(pyoracle.decodable(x + 3.0), np.log([[0.2, 0.8], [0.6, 0.4]]), atol=1e-12)
