@@ -218,8 +218,7 @@ ctcStatus_t b200ctc_decodable(const float *nnet_output, int input_is_logits, con
                               int alphabet_size, int minibatch, const float *priors, float prob_scale,
                               float blank_threshold, float floor_value, float *log_probs, int *kept_dev,
                               int *kept_host, void *workspace, size_t workspace_bytes, CUstream stream) {
-  if (!nnet_output || !input_lengths || !log_probs || !workspace || alphabet_size <= 0 || minibatch <= 0 ||
-      !(floor_value > 0.f))
+  if (!input_lengths || !workspace || alphabet_size <= 0 || minibatch <= 0 || !(floor_value > 0.f))
     return CTC_STATUS_INVALID_VALUE;
   int Tmax = 0;
   long total = 0;
@@ -237,6 +236,7 @@ ctcStatus_t b200ctc_decodable(const float *nnet_output, int input_is_logits, con
       return CTC_STATUS_EXECUTION_FAILED;
     return CTC_STATUS_SUCCESS;
   }
+  if (!nnet_output || !log_probs) return CTC_STATUS_INVALID_VALUE;
   char *w = static_cast<char *>(workspace);
   // lengths and output bases: pageable-source async copies are staged before the call returns
   int *base_h = new int[minibatch];

@@ -35,7 +35,9 @@ def test_kernel_matches_oracle(A, B, thr, use_priors, scale):
     x = _logits(rng, Tmax, B, A, 0.6)
     if B > 1:
         x[:, 1, 0] += 30.0     # utterance 1: every frame is blank-dominated -> "keep everything" corner (:62-63)
-    assert np.abs(_p_blank(x) - thr).min() > 1e-5 or thr >= 1.0
+    if thr < 1.0:   # keep every frame's decision clear of fp32 rounding: push borderline frames over
+        x[..., 0] += np.where(np.abs(_p_blank(x) / thr - 1.0) < 1e-2, 1.0, 0.0).astype(np.float32)
+        assert np.abs(_p_blank(x) / thr - 1.0).min() > 1e-4
     pri = (rng.random(A) + 0.05).astype(np.float32) if use_priors else None
     xd = torch.from_numpy(x.reshape(Tmax * B, A)).cuda()
     out, kept = decodable.decodable_log_probs(torch, xd, T, B, None if pri is None else torch.from_numpy(pri).cuda(),
@@ -82,9 +84,9 @@ def test_empty_and_invalid():
         decodable.decodable_log_probs(torch, x, [4], 1, floor=0.0)
 
 
-def _model(mode=2, H=32, layers=2):
+def _model(mode=2, H=32, layers=2, stddev=0.3):
     from kaldi_ctc_b200 import synth
-    spec = synth.ModelSpec(mode=mode, layers=layers, D=10, H=H, A=12, learning_rate=0.0, param_stddev=0.3)
+    spec = synth.ModelSpec(mode=mode, layers=layers, D=10, H=H, A=12, learning_rate=0.0, param_stddev=stddev)
     return spec, synth.model_weights(spec, 7)
 
 
@@ -133,7 +135,7 @@ def test_batched_decode_equals_per_utterance():
 
 def test_tensor_mode_decode_close_to_fp32():
     from kaldi_ctc_b200 import decodable, rnn
-    spec, (blobs, aw, ab) = _model(2, H=64, layers=2)
+    spec, (blobs, aw, ab) = _model(2, H=64, layers=2, stddev=0.1)
     rng = np.random.default_rng(6)
     feats = [rng.standard_normal((50, spec.D)).astype(np.float32) for _ in range(3)]
     a32 = decodable.AmNnet(spec, blobs, aw, ab, max_frames=64)
