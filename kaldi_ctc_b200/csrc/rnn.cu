@@ -520,7 +520,8 @@ b200rnnStatus_t b200rnnGemm(int transA, int transB, int M, int N, int K, float a
     int s = (int)std::min<size_t>(workspace_bytes / per, 32);
     const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
     if (s >= 2 && tiles < 148 && K >= 4096) {
-      g.splits = std::min(s, std::max(2, 296 / std::max(tiles, 1)));
+      // tensor mode: the most the workspace allows, the kernel's cost model picks the count
+      g.splits = math == B200RNN_MATH_TENSOR ? s : std::min(s, std::max(2, 296 / std::max(tiles, 1)));
       g.partial = static_cast<float *>(workspace);
     }
   }

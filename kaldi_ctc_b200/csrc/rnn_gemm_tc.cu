@@ -11,10 +11,16 @@
 //   pre = x . Wi^T   (A K-major, B K-major)     hoisted input projection
 //   dx  = dG . Wi    (A K-major, B MN-major)
 //   dW  = dG^T . x   (A MN-major, B MN-major), split-K with a fixed-order reduce
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA
-// issuer (one elected lane), warps 2-5 = epilogue (TMEM -> registers -> global).
-// 3-stage smem ring (96 KB) and 128 TMEM columns per CTA: two CTAs share an SM,
-// so one tile's epilogue overlaps the other's main loop.
+// Persistent kernel, one CTA per SM, dynamic tile scheduler:
+//   warp 0   = tile scheduler (atomic ticket -> smem tile queue) + TMA producer
+//   warp 1   = TMEM owner + MMA issuer (warp-uniform issue, one elected lane)
+//   warps 2-9 = epilogue (TMEM -> registers -> global), overlapped with the next tile's main
+//               loop through two TMEM accumulator buffers
+// Tiles are 128 x TBN with TBN = 256 when N > 128 (fp32 operands make the main loop L2->SMEM
+// bound: 48 KB per 2.1 MFLOP instead of 32 KB per 1.05 MFLOP), else 128.  ~192 KB smem ring.
+// The ticket counter makes the kernel indifferent to how many of its CTAs are resident: the
+// weight-gradient GEMMs run on a side stream next to the persistent recurrent kernels, which pin
+// 80 SMs for milliseconds; CTAs that only become resident later find the queue drained and exit.
 #include <stdio.h>
 
 #include "rnn_common.cuh"
@@ -25,11 +31,20 @@ namespace {
 
 using namespace tc;
 
-constexpr int TBM = 128, TBN = 128, TBK = 32;  // tf32: 32 elements = one 128-byte swizzle row
-constexpr int kStages = 3;
-constexpr int kTileBytes = TBM * TBK * 4;       // 16 KB per operand per stage
-constexpr int kThreads = 192;
-constexpr int kTmemCols = 128;
+constexpr int TBM = 128, TBK = 32;  // tf32: 32 elements = one 128-byte swizzle row
+constexpr int kABytes = TBM * TBK * 4;  // 16 KB
+constexpr int kEpiWarps = 8;            // two per TMEM lane quarter, each takes half of the tile's columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kQ = 4;                   // tile-queue depth
+
+template <int TBN>
+struct Cfg {
+  static constexpr int kBBytes = TBN * TBK * 4;            // 16 / 32 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;    // 32 / 48 KB
+  static constexpr int kStages = TBN == 256 ? 4 : 6;       // 192 KB either way
+  static constexpr int kTmemCols = 2 * TBN;                // two accumulator buffers
+  static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 512;
+};
 
 struct TcParams {
   int M, N, K;
@@ -40,38 +55,49 @@ struct TcParams {
   int nb;
   int splits, kb_per_split;
   float *partial;
+  int tiles_m, tiles_n, total;   // total = tiles_m * tiles_n * splits
+  int *ticket;                   // [0] next tile, [1] CTAs finished (both self-resetting)
 };
 
-template <bool A_KMAJOR, bool B_KMAJOR>
-__global__ void __launch_bounds__(kThreads, 2)
+template <bool A_KMAJOR, bool B_KMAJOR, int TBN>
+__global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+  using C = Cfg<TBN>;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  uint8_t *sA = smem;                         // [kStages][16 KB]
-  uint8_t *sB = smem + kStages * kTileBytes;  // [kStages][16 KB]
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + 2 * kStages * kTileBytes);
-  uint64_t *empty = full + kStages;
-  uint64_t *tmem_full = empty + kStages;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+  uint8_t *sA = smem;                           // [kStages][16 KB]
+  uint8_t *sB = smem + C::kStages * kABytes;    // [kStages][kBBytes]
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::kStages * C::kStageBytes);
+  uint64_t *empty = full + C::kStages;
+  uint64_t *acc_full = empty + C::kStages;   // [2]
+  uint64_t *acc_empty = acc_full + 2;        // [2]
+  uint64_t *q_full = acc_empty + 2;          // [kQ]
+  uint64_t *q_empty = q_full + kQ;           // [kQ]
+  int *tile_q = reinterpret_cast<int *>(q_empty + kQ);  // [kQ]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tile_q + kQ);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * TBN;
   const int nkb = (p.K + TBK - 1) / TBK;
-  const int kb0 = blockIdx.z * p.kb_per_split;
-  const int kb1 = min(nkb, kb0 + p.kb_per_split);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < kStages; s++) {
+    for (int s = 0; s < C::kStages; s++) {
       mbar_init(full + s, 1);
       mbar_init(empty + s, 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; b++) {
+      mbar_init(acc_full + b, 1);
+      mbar_init(acc_empty + b, kEpiWarps);
+    }
+    for (int q = 0; q < kQ; q++) {
+      mbar_init(q_full + q, 1);
+      mbar_init(q_empty + q, 1 + kEpiWarps);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_alloc(tmem_slot, C::kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -79,38 +105,75 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // tile id -> (split z, row tile, column tile); n fastest so that concurrently processed tiles
+  // share their A rows / B columns in L2
+  auto decode = [&](int tile, int &m0, int &n0, int &z, int &kb0, int &kb1) {
+    const int tn = tile % p.tiles_n;
+    const int r = tile / p.tiles_n;
+    const int tm = r % p.tiles_m;
+    z = r / p.tiles_m;
+    m0 = tm * TBM;
+    n0 = tn * TBN;
+    kb0 = z * p.kb_per_split;
+    kb1 = min(nkb, kb0 + p.kb_per_split);
+  };
+
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== tile scheduler + TMA producer =====
     if (lane == 0) {
-      for (int kb = kb0; kb < kb1; kb++) {
-        const int it = kb - kb0, s = it % kStages;
-        mbar_wait(empty + s, ((it / kStages) & 1) ^ 1);
-        mbar_expect_tx(full + s, 2 * kTileBytes);
-        uint8_t *a = sA + s * kTileBytes, *b = sB + s * kTileBytes;
-        if (A_KMAJOR) {
-          tma_load_2d(a, &tmA, kb * TBK, m0, full + s);
-        } else {
+      uint32_t it = 0;
+      for (uint32_t qi = 0;; qi++) {
+        int tile = atomicAdd(p.ticket, 1);
+        if (tile >= p.total) tile = -1;
+        mbar_wait(q_empty + (qi % kQ), ((qi / kQ) & 1) ^ 1);
+        tile_q[qi % kQ] = tile;
+        mbar_arrive(q_full + (qi % kQ));
+        if (tile < 0) break;
+        int m0, n0, z, kb0, kb1;
+        decode(tile, m0, n0, z, kb0, kb1);
+        for (int kb = kb0; kb < kb1; kb++, it++) {
+          const uint32_t s = it % C::kStages;
+          mbar_wait(empty + s, ((it / C::kStages) & 1) ^ 1);
+          mbar_expect_tx(full + s, C::kStageBytes);
+          uint8_t *a = sA + s * kABytes, *b = sB + s * C::kBBytes;
+          if (A_KMAJOR) {
+            tma_load_2d(a, &tmA, kb * TBK, m0, full + s);
+          } else {
 #pragma unroll
-          for (int j = 0; j < TBM / 32; j++) tma_load_2d(a + j * (TBK * 128), &tmA, m0 + j * 32, kb * TBK, full + s);
-        }
-        if (B_KMAJOR) {
-          tma_load_2d(b, &tmB, kb * TBK, n0, full + s);
-        } else {
+            for (int j = 0; j < TBM / 32; j++) tma_load_2d(a + j * (TBK * 128), &tmA, m0 + j * 32, kb * TBK, full + s);
+          }
+          if (B_KMAJOR) {
+            tma_load_2d(b, &tmB, kb * TBK, n0, full + s);
+          } else {
 #pragma unroll
-          for (int j = 0; j < TBN / 32; j++) tma_load_2d(b + j * (TBK * 128), &tmB, n0 + j * 32, kb * TBK, full + s);
+            for (int j = 0; j < TBN / 32; j++) tma_load_2d(b + j * (TBK * 128), &tmB, n0 + j * 32, kb * TBK, full + s);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc = instr_desc(kFmtTF32, A_KMAJOR ? 0 : 1, B_KMAJOR ? 0 : 1, TBM, TBN);
-    for (int kb = kb0; kb < kb1; kb++) {
-      const int it = kb - kb0, s = it % kStages;
-      mbar_wait(full + s, (it / kStages) & 1);
+    uint32_t it = 0, ai = 0;
+    for (uint32_t qi = 0;; qi++) {
+      mbar_wait(q_full + (qi % kQ), (qi / kQ) & 1);
+      const int tile = tile_q[qi % kQ];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_empty + (qi % kQ));
+      if (tile < 0) break;
+      int m0, n0, z, kb0, kb1;
+      decode(tile, m0, n0, z, kb0, kb1);
+      if (kb1 <= kb0) continue;  // empty split: the epilogue writes zeros
+      const uint32_t buf = ai & 1;
+      mbar_wait(acc_empty + buf, ((ai >> 1) & 1) ^ 1);
       tc_fence_after();
-      {
+      const uint32_t acc = tmem_base + buf * TBN;
+      for (int kb = kb0; kb < kb1; kb++, it++) {
+        const uint32_t s = it % C::kStages;
+        mbar_wait(full + s, (it / C::kStages) & 1);
+        tc_fence_after();
         // warp-uniform issue (descriptors stay in uniform registers), one elected lane issues
-        const uint32_t a = smem_u32(sA + s * kTileBytes), b = smem_u32(sB + s * kTileBytes);
+        const uint32_t a = smem_u32(sA + s * kABytes), b = smem_u32(sB + s * C::kBBytes);
 #pragma unroll
         for (int k = 0; k < TBK / 8; k++) {
           // K-major (SW128, 16 B chunks): 8-row groups are 1024 B apart (SBO); a K step of 8 tf32
@@ -122,75 +185,99 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                        : smem_desc(a + k * 1024, TBK * 128, 512, kLayoutSw128Base32);
           const uint64_t bd = B_KMAJOR ? smem_desc(b + k * 32, 0, 1024, kLayoutSw128)
                                        : smem_desc(b + k * 1024, TBK * 128, 512, kLayoutSw128Base32);
-          if (elect_one()) mma_tf32(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          if (elect_one()) mma_tf32(acc, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
         if (elect_one()) {
-          tc_commit(empty + s);                   // frees the smem stage when these MMAs retire
-          if (kb == kb1 - 1) tc_commit(tmem_full);  // accumulator complete
+          tc_commit(empty + s);                      // frees the smem stage when these MMAs retire
+          if (kb == kb1 - 1) tc_commit(acc_full + buf);  // accumulator complete
         }
+        __syncwarp();
       }
-      __syncwarp();
+      ai++;
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global =====
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
-    const int m = m0 + q * 32 + lane;
+    const int half = (warp - 2) >> 2;
     const bool direct = p.splits <= 1;
-    float *out = direct ? p.C : p.partial + (size_t)blockIdx.z * p.M * p.N;
     const int ldo = direct ? p.ldc : p.N;
-    const bool have = kb1 > kb0;
-    if (have) {
-      mbar_wait(tmem_full, 0);
-      tc_fence_after();
-    }
-    const bool vec_ok = (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-#pragma unroll 1
-    for (int c = 0; c < TBN / 32; c++) {
-      uint32_t r[32];
+    uint32_t ai = 0;
+    for (uint32_t qi = 0;; qi++) {
+      mbar_wait(q_full + (qi % kQ), (qi / kQ) & 1);
+      const int tile = tile_q[qi % kQ];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_empty + (qi % kQ));
+      if (tile < 0) break;
+      int m0, n0, z, kb0, kb1;
+      decode(tile, m0, n0, z, kb0, kb1);
+      const bool have = kb1 > kb0;
+      const uint32_t buf = ai & 1;
       if (have) {
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; j++) r[j] = 0u;
+        mbar_wait(acc_full + buf, (ai >> 1) & 1);
+        tc_fence_after();
       }
-      if (m < p.M) {
+      const int m = m0 + q * 32 + lane;
+      float *out = direct ? p.C : p.partial + (size_t)z * p.M * p.N;
+      const bool vec_ok = (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+      // Each lane owns one output row and writes it 16 bytes at a time; the eight stores of a chunk
+      // fill the lane's 128-byte line back to back and L2 merges them.  (A version that transposed
+      // through shared memory to store whole lines per instruction measured 10-25 % slower: the
+      // kernel is bound by the write path, not by store instructions.)
+#pragma unroll 1
+      for (int c = half * (TBN / 64); c < (half + 1) * (TBN / 64); c++) {
         const int nb0 = n0 + c * 32;
-        float *row = out + (size_t)m * ldo;
+        if (nb0 >= p.N) break;
+        uint32_t r[32];
+        if (have) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TBN + c * 32, r);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int j4 = 0; j4 < 8; j4++) {
-          const int n = nb0 + j4 * 4;
-          if (n >= p.N) break;
-          float v[4];
+          for (int j = 0; j < 32; j++) r[j] = 0u;
+        }
+        if (m < p.M) {
+          float *row = out + (size_t)m * ldo;
 #pragma unroll
-          for (int e = 0; e < 4; e++) v[e] = p.alpha * __uint_as_float(r[j4 * 4 + e]);
-          if (vec_ok && n + 3 < p.N) {
-            if (direct) {
-              if (p.beta != 0.f) {
-                const float4 o = *reinterpret_cast<const float4 *>(row + n);
-                v[0] += p.beta * o.x; v[1] += p.beta * o.y; v[2] += p.beta * o.z; v[3] += p.beta * o.w;
+          for (int j4 = 0; j4 < 8; j4++) {
+            const int n = nb0 + j4 * 4;
+            if (n >= p.N) break;
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) v[e] = p.alpha * __uint_as_float(r[j4 * 4 + e]);
+            if (vec_ok && n + 3 < p.N) {
+              if (direct) {
+                if (p.beta != 0.f) {
+                  const float4 o = *reinterpret_cast<const float4 *>(row + n);
+                  v[0] += p.beta * o.x; v[1] += p.beta * o.y; v[2] += p.beta * o.z; v[3] += p.beta * o.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                  if (p.bias_a) v[e] += p.bias_a[n + e];
+                  if (p.bias_b && n + e < p.nb) v[e] += p.bias_b[n + e];
+                }
               }
+              *reinterpret_cast<float4 *>(row + n) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
 #pragma unroll
               for (int e = 0; e < 4; e++) {
-                if (p.bias_a) v[e] += p.bias_a[n + e];
-                if (p.bias_b && n + e < p.nb) v[e] += p.bias_b[n + e];
+                if (n + e >= p.N) break;
+                float x = v[e];
+                if (direct) {
+                  if (p.beta != 0.f) x += p.beta * row[n + e];
+                  if (p.bias_a) x += p.bias_a[n + e];
+                  if (p.bias_b && n + e < p.nb) x += p.bias_b[n + e];
+                }
+                row[n + e] = x;
               }
-            }
-            *reinterpret_cast<float4 *>(row + n) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-              if (n + e >= p.N) break;
-              float x = v[e];
-              if (direct) {
-                if (p.beta != 0.f) x += p.beta * row[n + e];
-                if (p.bias_a) x += p.bias_a[n + e];
-                if (p.bias_b && n + e < p.nb) x += p.bias_b[n + e];
-              }
-              row[n + e] = x;
             }
           }
         }
+      }
+      if (have) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + buf);  // this warp's quarter of the buffer is drained
+        ai++;
       }
     }
   }
@@ -198,7 +285,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+  if (threadIdx.x == 0) {  // last CTA out re-arms the ticket for the next launch that uses this slot
+    __threadfence();
+    if (atomicAdd(p.ticket + 1, 1) == (int)gridDim.x - 1) {
+      p.ticket[0] = 0;
+      p.ticket[1] = 0;
+      __threadfence();
+    }
   }
 }
 
@@ -237,17 +332,52 @@ bool make_map(CUtensorMap *map, const float *base, long long inner, long long ou
   return r == CUDA_SUCCESS;
 }
 
-template <bool AK, bool BK>
-cudaError_t launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, dim3 grid, cudaStream_t s) {
-  const size_t smem = 1024 + 2 * kStages * kTileBytes + 128;
+// Self-resetting ticket slots, handed out round-robin: a slot is reused kTicketSlots launches later,
+// long after the launch that last used it has retired (the launch queue is far shallower).
+constexpr int kTicketSlots = 2048;
+
+int *ticket_slot() {
+  static int *base[64] = {};
+  static unsigned seq[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!base[dev]) {
+    if (cudaMalloc(&base[dev], sizeof(int) * 2 * kTicketSlots) != cudaSuccess) return nullptr;
+    if (cudaMemset(base[dev], 0, sizeof(int) * 2 * kTicketSlots) != cudaSuccess) return nullptr;
+  }
+  return base[dev] + 2 * (seq[dev]++ % kTicketSlots);
+}
+
+int sm_count() {
+  static int n[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (!n[dev]) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+  return n[dev] > 0 ? n[dev] : 148;
+}
+
+template <bool AK, bool BK, int TBN>
+cudaError_t launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, cudaStream_t s) {
+  const size_t smem = Cfg<TBN>::kSmem;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<AK, BK, TBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  tc_gemm_kernel<AK, BK><<<grid, kThreads, smem, s>>>(ta, tb, p);
+  const int grid = p.total < sm_count() ? p.total : sm_count();
+  tc_gemm_kernel<AK, BK, TBN><<<grid, kThreads, smem, s>>>(ta, tb, p);
   return cudaGetLastError();
+}
+
+template <int TBN>
+cudaError_t launch_any(bool ak, bool bk, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p,
+                       cudaStream_t s) {
+  if (ak && bk) return launch<true, true, TBN>(ta, tb, p, s);
+  if (ak) return launch<true, false, TBN>(ta, tb, p, s);
+  if (bk) return launch<false, true, TBN>(ta, tb, p, s);
+  return launch<false, false, TBN>(ta, tb, p, s);
 }
 
 }  // namespace
@@ -260,29 +390,54 @@ cudaError_t gemm_tc(const GemmArgs &g, cudaStream_t stream, int *launches) {
   const bool ak = g.sak == 1, bk = g.sbk == 1;
   if (!ak && g.sam != 1) return cudaErrorNotSupported;
   if (!bk && g.sbn != 1) return cudaErrorNotSupported;
+  // Tile width and split count from a small cost model: equal-length work items are handed out
+  // dynamically to SMs CTAs, so time ~ ceil(items / SMs) * (k-blocks per item * bytes staged per
+  // k-block + the item's share of epilogue traffic).  g.splits is the most the workspace allows.
+  static const int force_tbn = getenv("B200RNN_GEMM_TBN") ? atoi(getenv("B200RNN_GEMM_TBN")) : 0;
+  const int nkb = (g.K + TBK - 1) / TBK;
+  const int max_splits = (g.splits > 1 && g.partial) ? g.splits : 1;
+  const int sms = sm_count();
+  int tbn = 128, splits = 1;
+  double best = 1e300;
+  for (int w = 128; w <= 256; w += 128) {
+    if ((force_tbn == 128 || force_tbn == 256) && w != force_tbn) continue;
+    if (w == 256 && g.N <= 128) continue;
+    const long tiles = (long)((g.M + TBM - 1) / TBM) * ((g.N + w - 1) / w);
+    for (int sp = 1; sp <= max_splits; sp++) {
+      const int per = (nkb + sp - 1) / sp;
+      const int eff = (nkb + per - 1) / per;  // splits that actually get k-blocks
+      if (eff != sp) continue;
+      const long items = tiles * sp;
+      const double waves = items <= 3L * sms ? (double)((items + sms - 1) / sms) : (double)items / sms + 0.5;
+      const double cost = waves * ((double)per * (kABytes + w * TBK * 4) + 0.5 * TBM * w * 4) +
+                          (sp > 1 ? 2e-3 * sp * (double)g.M * g.N : 0.0);   // + the reduce pass
+      if (cost < best) {
+        best = cost;
+        tbn = w;
+        splits = sp;
+      }
+    }
+  }
   CUtensorMap ta, tb;
   const CUtensorMapSwizzle kmaj = CU_TENSOR_MAP_SWIZZLE_128B, mnmaj = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   bool ok = ak ? make_map(&ta, g.A, g.K, g.M, g.sam, TBK, TBM, kmaj)
                : make_map(&ta, g.A, g.M, g.K, g.sak, 32, TBK, mnmaj);
-  ok = ok && (bk ? make_map(&tb, g.B, g.K, g.N, g.sbn, TBK, TBN, kmaj)
+  ok = ok && (bk ? make_map(&tb, g.B, g.K, g.N, g.sbn, TBK, tbn, kmaj)
                  : make_map(&tb, g.B, g.N, g.K, g.sbk, 32, TBK, mnmaj));
   if (!ok) return cudaErrorNotSupported;
 
   TcParams p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.alpha = g.alpha; p.beta = g.beta;
   p.C = g.C; p.ldc = g.ldc; p.bias_a = g.bias_a; p.bias_b = g.bias_b; p.nb = g.nb;
-  const int nkb = (g.K + TBK - 1) / TBK;
-  int splits = (g.splits > 1 && g.partial) ? g.splits : 1;
   p.kb_per_split = (nkb + splits - 1) / splits;
-  splits = (nkb + p.kb_per_split - 1) / p.kb_per_split;
   p.splits = splits;
   p.partial = g.partial;
-  dim3 grid((g.N + TBN - 1) / TBN, (g.M + TBM - 1) / TBM, splits);
-  cudaError_t e;
-  if (ak && bk) e = launch<true, true>(ta, tb, p, grid, stream);
-  else if (ak) e = launch<true, false>(ta, tb, p, grid, stream);
-  else if (bk) e = launch<false, true>(ta, tb, p, grid, stream);
-  else e = launch<false, false>(ta, tb, p, grid, stream);
+  p.tiles_m = (g.M + TBM - 1) / TBM;
+  p.tiles_n = (g.N + tbn - 1) / tbn;
+  p.total = p.tiles_m * p.tiles_n * splits;
+  p.ticket = ticket_slot();
+  if (!p.ticket) return cudaErrorMemoryAllocation;
+  cudaError_t e = tbn == 256 ? launch_any<256>(ak, bk, ta, tb, p, stream) : launch_any<128>(ak, bk, ta, tb, p, stream);
   if (e != cudaSuccess) return e;
   if (launches) (*launches)++;
   if (splits > 1) {

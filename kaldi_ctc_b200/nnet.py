@@ -232,8 +232,12 @@ class NnetCtcUpdater:
         else:
             d = self.affine.Backprop(top_in, self.deriv[:rows], self.affine if update else None,
                                      in_deriv=self.dact[0][:rows])
+        pending = None
         for l in range(n - 1, -1, -1):
             d = self.clips[l].Backprop(d)
+            if pending is not None:   # layer l+1's weight GEMMs: released when the main stream gets here
+                pending.LaunchDeferredWeights()
+                pending = None
             inp = self.x_dev[:rows] if l == 0 else self.acts[l - 1][:rows]
             comp = self.rnns[l]
             if dp:
@@ -242,8 +246,10 @@ class NnetCtcUpdater:
                 red.submit([comp.filter_params_grad_],
                            lambda c=comp: c.Update(c.filter_params_grad_, c.clip_gradient_))
             else:
+                defer = update and comp.side_stream is not None and l > 0
                 d = comp.Backprop(inp, self.acts[l][:rows], d, to_update=comp if update else None,
-                                  want_in_deriv=(l > 0))
+                                  want_in_deriv=(l > 0), defer_weights=defer)
+                pending = comp if defer else None
         if dp:
             red.finish()
         if self.side_stream is not None:

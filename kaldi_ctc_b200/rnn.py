@@ -214,7 +214,11 @@ class CuDNNRecurrentComponent:
         self.launch_counts["fwd"] = self.plan.last_launches()
         return out
 
-    def Backprop(self, in_value, out_value, out_deriv, to_update=None, want_in_deriv=True):
+    def Backprop(self, in_value, out_value, out_deriv, to_update=None, want_in_deriv=True, defer_weights=False):
+        """defer_weights (side stream only): BackwardWeights + Update are not enqueued here but by
+        LaunchDeferredWeights(), which the caller invokes once the main stream holds everything up to
+        the NEXT component's recurrent kernel: the persistent GEMM CTAs must not grab the SMs before
+        that kernel's clusters are placed (a 10-CTA cluster needs most of a GPC)."""
         torch = self.torch
         T = in_value.shape[0] // self.mini_batch_
         assert 0 < T <= self.max_seq_length_ and out_deriv.is_contiguous()
@@ -228,13 +232,25 @@ class CuDNNRecurrentComponent:
                    "b200rnnBackwardData")
             self.launch_counts["bwd_data"] = self.plan.last_launches()
             if to_update is not None:
-                if self.side_stream is not None:
+                if self.side_stream is not None and defer_weights:
+                    self._deferred = (T, in_value, out_value, to_update)
+                elif self.side_stream is not None:
                     self.side_stream.wait_stream(torch.cuda.current_stream(self.device))
                     with torch.cuda.stream(self.side_stream):
                         self._backward_weights(T, in_value, out_value, to_update)
                 else:
                     self._backward_weights(T, in_value, out_value, to_update)
         return in_deriv
+
+    def LaunchDeferredWeights(self):
+        if getattr(self, "_deferred", None) is None:
+            return
+        torch = self.torch
+        args, self._deferred = self._deferred, None
+        with torch.cuda.device(self.device):
+            self.side_stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.side_stream):
+                self._backward_weights(*args)
 
     def _backward_weights(self, T, in_value, out_value, to_update):
         torch = self.torch
