@@ -21,7 +21,10 @@ SHAPES = [
 ]
 ws = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+only = sys.argv[1] if len(sys.argv) > 1 else None
 for name, tA, tB, M, N, K in SHAPES:
+    if only and not name.startswith(only):
+        continue
     A = torch.randn((K, M) if tA else (M, K), device="cuda")
     B = torch.randn((N, K) if tB else (K, N), device="cuda")
     C = torch.zeros(M, N, device="cuda")
