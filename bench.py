@@ -162,6 +162,26 @@ def ctc_roofline(dev, pk, pk_src, B=256):
             "l2": "inputs (12.3 GB) + outputs (12.3 GB) >> 126 MB L2"}
 
 
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel, from the committed
+    `ncu --set full` raw pages under profiles/ (captured once per change, never during a timed run)."""
+    import csv
+    import glob
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_raw.csv"))):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr, units = rows[0], rows[1]
+            ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            for r in rows[2:]:
+                if kernel_substr in r[ki]:
+                    return (float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]],
+                            "profiles/" + os.path.basename(path))
+        except (ValueError, IndexError, KeyError, OSError):
+            continue
+    return None, None
+
+
 def run_b200(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -237,8 +257,10 @@ def run_b200(args, rank, local_rank, world):
     avg_s = cat_ms[k] / max(cat_n[k], 1) / 1e3
     achieved = flops_per_launch / avg_s / 1e12 if avg_s > 0 else 0.0
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    traffic, traffic_src = ncu_traffic(["rec_tc_fwd", "rec_tc_bwd", "tc_gemm"][k])
     roofline = {"bound": "tensor", "kernel": names[k], "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": pk_src + " (bf16 sustained)",
+                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes/launch (dram read+write)",
+                "traffic_source": traffic_src, "peak_source": pk_src + " (bf16 sustained)",
                 "share_of_step": cat_ms[k] / ms_res,
                 "ms_per_step_by_kernel": {names[i]: cat_ms[i] / args.steps for i in range(3)}}
 
