@@ -219,10 +219,12 @@ class NnetCtcUpdater:
         it overlaps the lower layers' backward), then clipped and applied on every rank."""
         rows = T * self.B
         n = len(self.rnns)
+        t = self.torch
         top_in = self.acts[-1][:rows]
         dp = update and self.world > 1
-        for c in self.rnns:  # the all-reduce path keeps its own ordering: no side stream there
-            c.side_stream = None if dp else self.side_stream
+        side = self.side_stream
+        for c in self.rnns:
+            c.side_stream = side
         if dp:
             from .parallel import GradientReducer
             red = GradientReducer()
@@ -232,28 +234,48 @@ class NnetCtcUpdater:
         else:
             d = self.affine.Backprop(top_in, self.deriv[:rows], self.affine if update else None,
                                      in_deriv=self.dact[0][:rows])
-        pending = None
+        pending = None   # (component, what to run after its weight GEMMs) held back until the main stream
+        #                  has queued everything up to the next recurrent kernel
+
+        def release():
+            comp_, then_ = pending
+            comp_.LaunchDeferredWeights(then_)
+
         for l in range(n - 1, -1, -1):
             d = self.clips[l].Backprop(d)
-            if pending is not None:   # layer l+1's weight GEMMs: released when the main stream gets here
-                pending.LaunchDeferredWeights()
+            if pending is not None:
+                release()
                 pending = None
             inp = self.x_dev[:rows] if l == 0 else self.acts[l - 1][:rows]
             comp = self.rnns[l]
+            defer = update and side is not None and l > 0
             if dp:
-                grab = _Grab()
-                d = comp.Backprop(inp, self.acts[l][:rows], d, to_update=grab, want_in_deriv=(l > 0))
-                red.submit([comp.filter_params_grad_],
-                           lambda c=comp: c.Update(c.filter_params_grad_, c.clip_gradient_))
+                then = (lambda c=comp: red.submit([c.filter_params_grad_],
+                                                  lambda c=c: c.Update(c.filter_params_grad_, c.clip_gradient_)))
+                d = comp.Backprop(inp, self.acts[l][:rows], d, to_update=_Grab(), want_in_deriv=(l > 0),
+                                  defer_weights=defer)
+                if defer:
+                    pending = (comp, then)
+                elif side is not None:   # bottom layer: nothing left to hide under, but keep the stream order
+                    with t.cuda.stream(side):
+                        then()
+                else:
+                    then()
             else:
-                defer = update and comp.side_stream is not None and l > 0
                 d = comp.Backprop(inp, self.acts[l][:rows], d, to_update=comp if update else None,
                                   want_in_deriv=(l > 0), defer_weights=defer)
-                pending = comp if defer else None
+                pending = (comp, None) if defer else None
+        if pending is not None:
+            release()
         if dp:
-            red.finish()
-        if self.side_stream is not None:
-            self.torch.cuda.current_stream(self.device).wait_stream(self.side_stream)
+            if side is not None:
+                side.wait_stream(t.cuda.current_stream(self.device))
+                with t.cuda.stream(side):
+                    red.finish()
+            else:
+                red.finish()
+        if side is not None:
+            t.cuda.current_stream(self.device).wait_stream(side)
         return d
 
     def ComputeTotAccuracy(self, T, flat_labels, label_lengths, input_lengths):

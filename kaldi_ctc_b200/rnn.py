@@ -242,7 +242,8 @@ class CuDNNRecurrentComponent:
                     self._backward_weights(T, in_value, out_value, to_update)
         return in_deriv
 
-    def LaunchDeferredWeights(self):
+    def LaunchDeferredWeights(self, then=None):
+        """then: optional callable run on the side stream right after (the data-parallel all-reduce)."""
         if getattr(self, "_deferred", None) is None:
             return
         torch = self.torch
@@ -251,6 +252,8 @@ class CuDNNRecurrentComponent:
             self.side_stream.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self.side_stream):
                 self._backward_weights(*args)
+                if then is not None:
+                    then()
 
     def _backward_weights(self, T, in_value, out_value, to_update):
         torch = self.torch
