@@ -15,7 +15,8 @@ from kaldi_ctc_b200 import nnet, parallel, rnn, synth  # noqa: E402
 
 math = rnn.MATH_TENSOR if (len(sys.argv) > 1 and sys.argv[1] == "tensor") else rnn.MATH_FP32
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dev = "cuda:%d" % int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(dev)
 dist.init_process_group("nccl")
 Bl, T = 4, 48
 spec = synth.ModelSpec(mode=2, layers=3, D=16, H=64, A=20, learning_rate=0.01, param_stddev=0.2)
@@ -27,14 +28,14 @@ x3 = x.reshape(T, Bt, spec.D)
 offs = np.concatenate([[0], np.cumsum(L)])
 xl = np.ascontiguousarray(x3[:, mine]).reshape(T * Bl, spec.D)
 fll = np.concatenate([fl[offs[b]:offs[b + 1]] for b in mine])
-up = nnet.NnetCtcUpdater(spec, blobs, aw, ab, Bl, T, math=math, world=world)
+up = nnet.NnetCtcUpdater(spec, blobs, aw, ab, Bl, T, device=dev, math=math, world=world)
 steps = 2
 for _ in range(steps):
     objf = up.ComputeForMinibatch(torch.from_numpy(xl).pin_memory(), T, fll, L[mine], Tl[mine])
 tot = parallel.reduce_scalar_sum(objf, device="cuda")
 ok = True
 if rank == 0:
-    ref = nnet.NnetCtcUpdater(spec, blobs, aw, ab, Bt, T, math=math, world=1)
+    ref = nnet.NnetCtcUpdater(spec, blobs, aw, ab, Bt, T, device=dev, math=math, world=1)
     for _ in range(steps):
         objf_ref = ref.ComputeForMinibatch(torch.from_numpy(x).pin_memory(), T, fl, L, Tl)
     tol = 2e-5 if math == rnn.MATH_FP32 else 2e-3
