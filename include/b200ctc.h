@@ -83,6 +83,31 @@ ctcStatus_t b200ctc_decodable(const float *nnet_output, int input_is_logits,
                               int *kept_host, void *workspace, size_t workspace_bytes,
                               CUstream stream);
 
+/*
+ * Training input path: kaldi::ctc::FormatNnetInput
+ * (src/ctc/ctc-nnet-update.cc:351-424) with the CompressedMatrix decompression
+ * (src/matrix/compressed-matrix.cc:493-529, bit-exact) moved onto the GPU, so that the compressed
+ * bytes are what crosses PCIe.
+ * examples_host[m]: HOST pointer to data[m].input_frames' in-memory image (CompressedMatrix::data_:
+ *   GlobalHeader{int32 format; float min_value, range; int32 num_rows, num_cols}, then format 1:
+ *   PerColHeader[num_cols] + bytes column-major, format 2: uint16 row-major; compressed-matrix.h:128-143).
+ * spk_info_host[m]: HOST data[m].spk_info (spk_dim floats; the array may be NULL when spk_dim == 0).
+ * left_context = data[0].left_context; nnet_left/right_context = nnet.LeftContext()/RightContext().
+ * input_mat: DEVICE [max_num_frames * num_splice * minibatch, feat_dim + spk_dim], row
+ *   (t*minibatch + m)*num_splice + s, padding rows zeroed -- exactly *input_mat of the reference.
+ * staging_host (pinned recommended) / staging_dev: staging_bytes each, from b200ctc_format_input_size.
+ *   The call packs into staging_host and enqueues ONE host-to-device copy + one kernel on `stream`;
+ *   staging_host must stay untouched until the stream has passed the copy (alternate two buffers).
+ */
+ctcStatus_t b200ctc_format_input_size(const void *const *examples_host, int minibatch, int spk_dim,
+                                      int left_context, int nnet_left_context, int nnet_right_context,
+                                      int *max_num_frames, int *feat_dim, size_t *staging_bytes);
+ctcStatus_t b200ctc_format_input(const void *const *examples_host, const float *const *spk_info_host,
+                                 int spk_dim, int minibatch, int left_context, int nnet_left_context,
+                                 int nnet_right_context, float *input_mat, size_t input_mat_floats,
+                                 void *staging_host, void *staging_dev, size_t staging_bytes,
+                                 CUstream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -160,6 +160,7 @@ class NnetCtcUpdater:
         self.costs_dev = t.zeros(minibatch, device=self.device)
         self.costs_host = t.zeros(minibatch, dtype=t.float32).pin_memory()
         self.best_pdf = None       # [rows] int32, filled by the CTC pass when accuracy is wanted
+        self.stager = None         # pinned/device staging of the compressed minibatch (egs.InputStager)
         self.best_pdf_host = None
         # The weight-gradient GEMMs of layer l (and its clip+update / all-reduce) do not feed layer l-1's
         # backward: they run on a side stream under the (latency-bound, 80-SM) recurrent kernel of the
@@ -182,6 +183,32 @@ class NnetCtcUpdater:
         """feats_host: pinned [T*B, D] float32 (FormatNnetInput's output) -> device."""
         rows = T * self.B
         self.x_dev[:rows].copy_(feats_host[:rows], non_blocking=True)
+
+    def FormatInputFromExamples(self, examples):
+        """FormatNnetInput on the GPU (b200ctc_format_input): the compressed frames are what crosses PCIe.
+        Returns (T, flat_labels, label_lengths, input_lengths) of the minibatch (:351-424, :171-206)."""
+        from . import egs
+        if self.stager is None:
+            self.stager = egs.InputStager(self.device)
+        assert len(examples) == self.B
+        _, T = egs.FormatNnetInput(0, 0, examples, input_mat=self.x_dev, stager=self.stager)
+        assert T <= self.max_frames
+        ignore = examples[0].left_context
+        il = np.array([eg.NumFrames() - ignore for eg in examples], dtype=np.int32)
+        ll = np.array([eg.NumLabels() for eg in examples], dtype=np.int32)
+        fl = np.concatenate([np.asarray(eg.labels, dtype=np.int32) for eg in examples])
+        return T, fl, ll, il
+
+    def ComputeForMinibatchFromExamples(self, examples, update=True, host_sync=True, want_best_pdf=False):
+        """NnetCtcUpdater::ComputeForMinibatch(const std::vector<NnetCtcExample>&, ...) (:94-117)."""
+        t = self.torch
+        cur = t.cuda.current_stream(self.device)
+        self.main_stream.wait_stream(cur)
+        with t.cuda.stream(self.main_stream):
+            T, fl, ll, il = self.FormatInputFromExamples(examples)
+        cur.wait_stream(self.main_stream)
+        return self.ComputeForMinibatch(None, T, fl, ll, il, update=update, host_sync=host_sync,
+                                        want_best_pdf=want_best_pdf)
 
     def Propagate(self, T):
         rows = T * self.B

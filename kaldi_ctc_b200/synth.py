@@ -115,3 +115,18 @@ def features(B, D, t_lo, t_hi, l_lo, l_hi, A, seed):
         x[T[b]:, b, :] = 0.0
     labels = [rng.integers(1, A, size=int(l)).astype(np.int32) for l in L]
     return x.reshape(Tmax * B, D), np.concatenate(labels).astype(np.int32), L, T
+
+
+def examples(B, D, t_lo, t_hi, l_lo, l_hi, A, seed, left_context=0, spk_dim=0):
+    """The same kind of minibatch as features(), as the reference stores it on disk: one
+    NnetCtcExample per utterance with CompressedMatrix frames (egs.py)."""
+    from . import egs
+    rng = np.random.Generator(np.random.PCG64(seed))
+    T, L = _lengths(rng, B, t_lo, t_hi, l_lo, l_hi)
+    out = []
+    for b in range(B):
+        frames = rng.standard_normal((int(T[b]) + left_context, D), dtype=np.float32)
+        labels = rng.integers(1, A, size=int(L[b])).astype(np.int32)
+        spk = rng.standard_normal(spk_dim).astype(np.float32) if spk_dim else []
+        out.append(egs.NnetCtcExample(labels, egs.CompressedMatrix.from_matrix(frames), left_context, spk))
+    return out

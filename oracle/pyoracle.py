@@ -147,3 +147,49 @@ def decodable(nnet_output, prob_scale=1.0, blank_threshold=1.0, priors=None, flo
     if priors is not None:
         lp = lp - np.log(np.asarray(priors, dtype=dtype))[None, :]   # :76-81
     return lp * dtype(prob_scale)                   # :83
+
+
+# ---- training input path (oracle/feat_oracle.c) ---------------------------------------------------
+def cm_compress(mat, force_format=0):
+    """CompressedMatrix::CopyFromMat -> the in-memory image as bytes (b"" for an empty matrix)."""
+    mat = np.ascontiguousarray(mat, dtype=np.float32)
+    rows, cols = mat.shape
+    if rows == 0 or cols == 0:
+        return b""
+    L = lib()
+    L.feat_oracle_data_size.restype = ctypes.c_long
+    L.feat_oracle_compress.restype = ctypes.c_long
+    fmt = force_format or (1 if rows > 8 else 2)
+    out = np.zeros(L.feat_oracle_data_size(fmt, rows, cols), dtype=np.uint8)
+    n = L.feat_oracle_compress(_p(mat), rows, cols, cols, force_format, _p(out))
+    assert n == out.size
+    return out.tobytes()
+
+
+def cm_decompress(blob):
+    """CompressedMatrix::CopyToMat -> float32 [rows, cols]."""
+    fmt, _, _, rows, cols = np.frombuffer(blob[:20], dtype=[("f", "<i4"), ("a", "<f4"), ("b", "<f4"),
+                                                            ("r", "<i4"), ("c", "<i4")])[0]
+    out = np.zeros((int(rows), int(cols)), dtype=np.float32)
+    buf = np.frombuffer(blob, dtype=np.uint8)
+    assert lib().feat_oracle_decompress(_p(buf), _p(out)) == 0
+    return out
+
+
+def format_nnet_input(blobs, spk_infos, left_context, nnet_left, nnet_right):
+    """kaldi::ctc::FormatNnetInput -> (input_mat [max_frames*num_splice*B, tot_dim] float32, max_frames)."""
+    B = len(blobs)
+    bufs = [np.frombuffer(b, dtype=np.uint8) for b in blobs]
+    ptrs = (ctypes.c_void_p * B)(*[b.ctypes.data for b in bufs])
+    spk_dim = 0 if spk_infos is None else int(np.asarray(spk_infos[0]).size)
+    spks = [np.ascontiguousarray(s, dtype=np.float32) for s in (spk_infos or [])]
+    sptr = (ctypes.c_void_p * B)(*[s.ctypes.data for s in spks]) if spk_dim else None
+    rows = max(int(np.frombuffer(b[12:16], dtype="<i4")[0]) for b in blobs)
+    cols = int(np.frombuffer(blobs[0][16:20], dtype="<i4")[0]) + spk_dim
+    S = 1 + nnet_left + nnet_right
+    out = np.empty(rows * S * B * cols, dtype=np.float32)
+    mf = lib().feat_oracle_format_nnet_input(ptrs, sptr, spk_dim, B, left_context, nnet_left, nnet_right,
+                                             _p(out), ctypes.c_long(out.size))
+    if mf < 0:
+        raise ValueError("FormatNnetInput: bad input")
+    return out[:mf * S * B * cols].reshape(mf * S * B, cols).copy(), mf
