@@ -200,7 +200,12 @@ def run_b200(args, rank, local_rank, world):
     feats = torch.from_numpy(x).pin_memory()
     valid_frames = int(T.sum())
 
+    # the same minibatch as the reference holds it on the host: NnetCtcExamples with compressed frames
+    egs_batch = synth.examples(B, spec.D, 1200, 2000, 120, 180, spec.A, seed=1002 + 97 * rank)
+
     def step(resident):
+        if resident == "egs":     # ComputeForMinibatch(const std::vector<NnetCtcExample>&): GPU FormatNnetInput
+            return up.ComputeForMinibatchFromExamples(egs_batch, host_sync=True)
         if resident:
             return up.ComputeForMinibatch(None, Tmax, fl, L, T, host_sync=False)
         return up.ComputeForMinibatch(feats, Tmax, fl, L, T, host_sync=True)
@@ -237,6 +242,10 @@ def run_b200(args, rank, local_rank, world):
     sampler.join()
     ms_e2e = timed(False, args.steps)
     objf = up.last_objf()
+    for _ in range(args.warmup):
+        step("egs")
+    ms_egs = timed("egs", args.steps)
+    egs_frames = int(sum(e.NumFrames() for e in egs_batch))
 
     # ---- roofline of the dominant kernel (CUDA events recorded inside the timed region)
     pk, pk_src = peaks()
@@ -278,6 +287,10 @@ def run_b200(args, rank, local_rank, world):
                    "l2": "working set per step (activations+reserve ~2.5 GB) >> 126 MB L2; no explicit flush"},
         "e2e": {"value": valid_frames * world * args.steps / (ms_e2e / 1e3), "unit": UNIT,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "e2e_from_examples": {"value": egs_frames * world * args.steps / (ms_egs / 1e3), "unit": UNIT,
+                              "h2d_bytes_per_step": int(up.stager.h2d_bytes), "d2h_bytes_per_step": d2h,
+                              "ms_per_step": ms_egs / args.steps, "valid_frames_per_step": egs_frames * world,
+                              "what": "host NnetCtcExamples (CompressedMatrix frames) -> GPU decompress+format -> step"},
         "gpu_launches": up.launches_per_step() * args.steps,
         "clocks": sampler.summary(),
         "roofline": roofline,

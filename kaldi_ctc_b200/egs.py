@@ -254,9 +254,12 @@ class InputStager:
         t, k = self.torch, self.k
         if self.host[k] is None or self.host[k].numel() < nbytes:
             cap = int(nbytes * 1.25) + 4096
-            self.host[k] = t.empty(cap, dtype=t.uint8).pin_memory()
-            self.dev[k] = t.empty(cap, dtype=t.uint8, device=self.device)
-            self.done[k] = None
+            for j in (0, 1):   # both halves at once: pinning is slow, keep it out of the steady state
+                if self.done[j] is not None:
+                    self.done[j].synchronize()
+                self.host[j] = t.empty(cap, dtype=t.uint8).pin_memory()
+                self.dev[j] = t.empty(cap, dtype=t.uint8, device=self.device)
+                self.done[j] = None
         if self.done[k] is not None:
             self.done[k].synchronize()  # the upload that last used this pair has completed
         return self.host[k], self.dev[k]
