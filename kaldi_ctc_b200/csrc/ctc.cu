@@ -258,6 +258,175 @@ ctc_rowstats_gather_kernel(CtcDev d) {
 //   X_i <- El_i + lse(X_i, Y_i, skip_i ? X_{i-1} : 0)
 // alpha: Y_i = state 2i, X_i = state 2i+1, time ascending, label i.
 // beta : Y_i = state 2(L-i), X_i = state 2(L-i)-1, time descending, label L-1-i.
+// The per-frame loop is ISSUE-bound as much as latency-bound (a first version spent ~225 SASS
+// instructions per frame on index arithmetic: step / F, step % 8, role selects, 64-bit address
+// rebuilds), so the role is a template parameter and every index advances incrementally.
+template <int P, int ROLE>
+__device__ __forceinline__ void ctc_ab_run(const CtcDev &d, const UttMeta &um, int b, int r, int nthreads_needed,
+                                           int nbar, uint64_t *my_bar, float *my_stage, float2 *bnd, float *fin,
+                                           int F) {
+  const int lane = r & 31, w = r >> 5;
+  const int L = um.L, T = um.T, pitch = um.pitch;
+  const float *Eg = d.E + um.e_off;
+  const int nchunks = (T + F - 1) / F;
+
+  // chunk k (in visiting order) -> first frame and frame count
+  auto chunk_lo = [&](int k) { return ROLE ? max(0, T - (k + 1) * F) : k * F; };
+  auto chunk_n = [&](int k) { return min(F, T - k * F); };
+  auto issue = [&](int k) {
+    const int st = k % kStages;
+    const uint32_t bytes = (uint32_t)chunk_n(k) * pitch * 4u;
+    mbar_expect_tx(my_bar + st, bytes);
+    tma_load_1d(my_stage + st * kStageFloats, Eg + (long long)chunk_lo(k) * pitch, bytes, my_bar + st);
+  };
+  if (r == 0)
+    for (int k = 0; k < min(kStages, nchunks); k++) issue(k);
+
+  // per-thread lattice slice
+  const int i0 = r * P;
+  const int *lab = d.labels + um.lab_off;
+  float X[P], Y[P];
+  int eidx[P];      // index of El_i inside a frame of E
+  int soff[P];      // float offset of this pair inside a stored frame
+  bool skip[P], hasX[P], hasY[P];
+#pragma unroll
+  for (int p = 0; p < P; p++) {
+    const int i = i0 + p;
+    hasY[p] = i <= L;
+    hasX[p] = i < L;
+    int li = 0, lprev = -1;
+    if (hasX[p]) {
+      li = ROLE ? lab[L - 1 - i] : lab[i];
+      if (i >= 1) lprev = ROLE ? lab[L - i] : lab[i - 1];
+    }
+    skip[p] = hasX[p] && i >= 1 && li != lprev;
+    eidx[p] = hasX[p] ? (ROLE ? L - i : 1 + i) : 0;
+    soff[p] = hasY[p] ? (ROLE ? 2 * (L - i) : 2 * i) : 0;
+    X[p] = kNeg;
+    Y[p] = (i == 0) ? 0.f : kNeg;  // virtual frame "-1": all mass on the first blank
+  }
+  // Values are kept relative to a per-thread integer offset c (a float holding an
+  // integer): true log2 value = stored + c.  A thread whose states are all still
+  // unreachable simply adopts its neighbour's offset.
+  float xin = kNeg;  // X_{i0-1} of the previous frame, already relative to c
+  float c = 0.f;
+  bool live = (r == 0);
+
+  const int pitch2 = 2 * pitch;
+  float *o = (ROLE ? d.beta : d.alpha) + um.ab_off + (ROLE ? (long long)(T - 1) * pitch2 : 0);
+  float *off_out = (ROLE ? d.offB : d.offA) + um.off_off + r;
+  const int o_step = ROLE ? -pitch2 : pitch2, e_step = ROLE ? -pitch : pitch;
+  const bool writes_off = r < nthreads_needed;
+  float2 *bn_w = bnd + w;          // this warp's slot; the double buffer toggles by +-32
+  int par = 0, rn = kRenorm, st = 0;
+  uint32_t ph = 0;
+
+  for (int k = 0; k < nchunks; k++) {
+    const int n = min(F, T - k * F);
+    mbar_wait(my_bar + st, ph);
+    const float *e = my_stage + st * kStageFloats + (ROLE ? (n - 1) * pitch : 0);
+    const bool last_chunk = k == nchunks - 1;
+    for (int f = 0; f < n; f++) {
+      const float Eb = e[0];
+      float El[P];
+#pragma unroll
+      for (int p = 0; p < P; p++) El[p] = hasX[p] ? e[eidx[p]] : kNeg;  // kNeg keeps a missing X at "log 0"
+      e += e_step;
+
+      float nX[P], nY[P];
+#pragma unroll
+      for (int p = 0; p < P; p++) {
+        const float xp = p == 0 ? xin : X[p - 1];
+        nY[p] = Eb + lse2_2(Y[p], xp);
+        nX[p] = El[p] + lse2_3(X[p], Y[p], skip[p] ? xp : kNeg);
+      }
+#pragma unroll
+      for (int p = 0; p < P; p++) {
+        Y[p] = nY[p];
+        X[p] = nX[p];
+      }
+      // store this frame (relative to c)
+#pragma unroll
+      for (int p = 0; p < P; p++)
+        if (hasY[p])
+          *reinterpret_cast<float2 *>(o + soff[p]) = ROLE ? make_float2(X[p], Y[p]) : make_float2(Y[p], X[p]);
+      o += o_step;
+      // end of a frame block: publish the offset the block was stored with, re-centre.  c only changes
+      // here: re-centred if the thread has reachable states, otherwise adopted from the left neighbour.
+      const bool block_end = (--rn == 0) || (last_chunk && f == n - 1);
+      if (block_end) {
+        rn = kRenorm;
+        if (writes_off) *off_out = c;
+        off_out += nthreads_needed;
+        float mx = kNeg;
+#pragma unroll
+        for (int p = 0; p < P; p++) mx = fmaxf(mx, fmaxf(hasX[p] ? X[p] : kNeg, hasY[p] ? Y[p] : kNeg));
+        live = mx > -1.0e29f;
+        if (live) {
+          const float sh = floorf(mx);
+#pragma unroll
+          for (int p = 0; p < P; p++) {
+            X[p] = fmaxf(X[p] - sh, kNeg);
+            Y[p] = fmaxf(Y[p] - sh, kNeg);
+          }
+          c += sh;
+        }
+      }
+      // hand (X_last, c) to the next thread for the next frame
+      const float xs = __shfl_up_sync(0xffffffffu, X[P - 1], 1);
+      const float cs = __shfl_up_sync(0xffffffffu, c, 1);
+      if (lane == 31) bn_w[par] = make_float2(X[P - 1], c);
+      named_bar_sync(1 + ROLE, nbar);
+      float xv = xs, cv = cs;
+      if (lane == 0) {
+        const float2 v = w == 0 ? make_float2(kNeg, c) : bn_w[par - 1];
+        xv = v.x;
+        cv = v.y;
+      }
+      par ^= 32;
+      if (block_end && !live) c = cv;    // nothing reachable here yet: follow the neighbour
+      xin = fmaxf(xv + (cv - c), kNeg);  // cv - c is an exact integer
+    }
+    // stage fully consumed (every thread is past the barrier of its last frame) -> refill it
+    if (r == 0 && k + kStages < nchunks) issue(k + kStages);
+    if (++st == kStages) {
+      st = 0;
+      ph ^= 1;
+    }
+  }
+
+  // log2 p(l|x) = lse(Y_L, X_{L-1}) in absolute terms
+#pragma unroll
+  for (int p = 0; p < P; p++) {
+    const int i = i0 + p;
+    if (i == L) {
+      fin[0] = Y[p];
+      fin[1] = c;
+    }
+    if (i == L - 1) {
+      fin[2] = X[p];
+      fin[3] = c;
+    }
+  }
+  if (r == 0 && L == 0) {
+    fin[2] = kNeg;
+    fin[3] = 0.f;
+  }
+  named_bar_sync(1 + ROLE, nbar);
+  if (r == 0) {
+    const double v0 = (double)fin[0] + (double)fin[1];
+    const double v1 = (double)fin[2] + (double)fin[3];
+    const double hi = fmax(v0, v1), lo = fmin(v0, v1);
+    const double lp2 = hi + log2(1.0 + exp2(fmax(lo - hi, -1000.0)));
+    d.logp2[ROLE * d.B + b] = lp2;
+    if (ROLE == 0) {
+      const float cost = (float)(-lp2 * kLn2);
+      d.costs[b] = cost;
+      if (!(fabsf(cost) < 3.0e38f)) atomicOr(d.flags, 1);
+    }
+  }
+}
+
 template <int P>
 __global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int frames_per_stage) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -272,8 +441,6 @@ __global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int f
   const int NT = blockDim.x >> 1;
   const int role = threadIdx.x >= NT ? 1 : 0;
   const int r = threadIdx.x - role * NT;
-  const int lane = r & 31, w = r >> 5;
-  const int L = um.L, T = um.T, pitch = um.pitch, F = frames_per_stage;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2 * kStages; i++) mbar_init(mbar + i, 1);
@@ -281,163 +448,15 @@ __global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int f
   }
   __syncthreads();
 
-  const int nthreads_needed = (L + 1 + P - 1) / P;
+  const int nthreads_needed = (um.L + 1 + P - 1) / P;
   const int nwarps_active = (nthreads_needed + 31) >> 5;
-  if (w >= nwarps_active) return;  // idle warps leave; named barriers count the rest
+  if ((r >> 5) >= nwarps_active) return;  // idle warps leave; named barriers count the rest
   const int nbar = nwarps_active * 32;
-
-  uint64_t *my_bar = mbar + role * kStages;
-  float *my_stage = stages + role * kStages * kStageFloats;
-  const float *Eg = d.E + um.e_off;
-  const int nchunks = (T + F - 1) / F;
-
-  // chunk k (in visiting order) -> first frame and frame count
-  auto chunk_lo = [&](int k) { return role ? max(0, T - (k + 1) * F) : k * F; };
-  auto chunk_n = [&](int k) { return min(F, T - k * F); };
-  auto issue = [&](int k) {
-    const int st = k % kStages;
-    const uint32_t bytes = (uint32_t)chunk_n(k) * pitch * 4u;
-    mbar_expect_tx(my_bar + st, bytes);
-    tma_load_1d(my_stage + st * kStageFloats, Eg + (long long)chunk_lo(k) * pitch, bytes,
-                my_bar + st);
-  };
-  if (r == 0)
-    for (int k = 0; k < min(kStages, nchunks); k++) issue(k);
-
-  // per-thread lattice slice
-  const int i0 = r * P;
-  const int *lab = d.labels + um.lab_off;
-  float X[P], Y[P];
-  int eidx[P];      // index of El_i inside a frame of E
-  bool skip[P], hasX[P], hasY[P];
-#pragma unroll
-  for (int p = 0; p < P; p++) {
-    const int i = i0 + p;
-    hasY[p] = i <= L;
-    hasX[p] = i < L;
-    int li = 0, lprev = -1;
-    if (hasX[p]) {
-      li = role ? lab[L - 1 - i] : lab[i];
-      if (i >= 1) lprev = role ? lab[L - i] : lab[i - 1];
-    }
-    skip[p] = hasX[p] && i >= 1 && li != lprev;
-    eidx[p] = hasX[p] ? (role ? L - i : 1 + i) : 0;
-    X[p] = kNeg;
-    Y[p] = (i == 0) ? 0.f : kNeg;  // virtual frame "-1": all mass on the first blank
-  }
-  // Values are kept relative to a per-thread integer offset c (a float holding an
-  // integer): true log2 value = stored + c.  A thread whose states are all still
-  // unreachable simply adopts its neighbour's offset.
-  float xin = kNeg;  // X_{i0-1} of the previous frame, already relative to c
-  float c = 0.f;
-  bool live = (r == 0);
-
-  float *out = (role ? d.beta : d.alpha) + um.ab_off;
-  float *off_out = (role ? d.offB : d.offA) + um.off_off;
-  const int pitch2 = 2 * pitch;
-
-  for (int step = 0; step < T; step++) {
-    const int t = role ? T - 1 - step : step;
-    const int k = step / F;
-    const int st = k % kStages;
-    if (step - k * F == 0) mbar_wait(my_bar + st, (k / kStages) & 1);
-    const float *e = my_stage + st * kStageFloats + (t - chunk_lo(k)) * pitch;
-    const float Eb = e[0];
-    float El[P];
-#pragma unroll
-    for (int p = 0; p < P; p++) El[p] = hasX[p] ? e[eidx[p]] : kNeg;  // kNeg keeps a missing X at "log 0"
-
-    float nX[P], nY[P];
-#pragma unroll
-    for (int p = 0; p < P; p++) {
-      const float xp = p == 0 ? xin : X[p - 1];
-      nY[p] = Eb + lse2_2(Y[p], xp);
-      nX[p] = El[p] + lse2_3(X[p], Y[p], skip[p] ? xp : kNeg);
-    }
-#pragma unroll
-    for (int p = 0; p < P; p++) {
-      Y[p] = nY[p];
-      X[p] = nX[p];
-    }
-    // store this frame (relative to c)
-    float *o = out + (long long)t * pitch2;
-#pragma unroll
-    for (int p = 0; p < P; p++) {
-      const int i = i0 + p;
-      if (hasY[p]) {
-        if (role == 0)
-          *reinterpret_cast<float2 *>(o + 2 * i) = make_float2(Y[p], X[p]);
-        else
-          *reinterpret_cast<float2 *>(o + 2 * (L - i)) = make_float2(X[p], Y[p]);
-      }
-    }
-    // end of a frame block: publish the offset the block was stored with, re-centre.  c only changes
-    // here: re-centred if the thread has reachable states, otherwise adopted from the left neighbour.
-    const bool block_end = (step % kRenorm) == kRenorm - 1 || step == T - 1;
-    if (block_end) {
-      if (r < nthreads_needed) off_out[(step / kRenorm) * nthreads_needed + r] = c;
-      float mx = kNeg;
-#pragma unroll
-      for (int p = 0; p < P; p++) mx = fmaxf(mx, fmaxf(hasX[p] ? X[p] : kNeg, hasY[p] ? Y[p] : kNeg));
-      live = mx > -1.0e29f;
-      if (live) {
-        const float sh = floorf(mx);
-#pragma unroll
-        for (int p = 0; p < P; p++) {
-          X[p] = fmaxf(X[p] - sh, kNeg);
-          Y[p] = fmaxf(Y[p] - sh, kNeg);
-        }
-        c += sh;
-      }
-    }
-    // hand (X_last, c) to the next thread for the next frame
-    const float xs = __shfl_up_sync(0xffffffffu, X[P - 1], 1);
-    const float cs = __shfl_up_sync(0xffffffffu, c, 1);
-    float2 *bn = bnd + (role * 2 + (step & 1)) * 32;
-    if (lane == 31) bn[w] = make_float2(X[P - 1], c);
-    named_bar_sync(1 + role, nbar);
-    float xv = xs, cv = cs;
-    if (lane == 0) {
-      const float2 v = w == 0 ? make_float2(kNeg, c) : bn[w - 1];
-      xv = v.x;
-      cv = v.y;
-    }
-    if (block_end && !live) c = cv;    // nothing reachable here yet: follow the neighbour
-    xin = fmaxf(xv + (cv - c), kNeg);  // cv - c is an exact integer
-    // stage fully consumed -> refill it with the chunk kStages ahead
-    if (r == 0 && (step + 1 == (k + 1) * F) && k + kStages < nchunks) issue(k + kStages);
-  }
-
-  // log2 p(l|x) = lse(Y_L, X_{L-1}) in absolute terms
-#pragma unroll
-  for (int p = 0; p < P; p++) {
-    const int i = i0 + p;
-    if (i == L) {
-      fin[role * 4 + 0] = Y[p];
-      fin[role * 4 + 1] = c;
-    }
-    if (i == L - 1) {
-      fin[role * 4 + 2] = X[p];
-      fin[role * 4 + 3] = c;
-    }
-  }
-  if (r == 0 && L == 0) {
-    fin[role * 4 + 2] = kNeg;
-    fin[role * 4 + 3] = 0.f;
-  }
-  named_bar_sync(1 + role, nbar);
-  if (r == 0) {
-    const double v0 = (double)fin[role * 4 + 0] + (double)fin[role * 4 + 1];
-    const double v1 = (double)fin[role * 4 + 2] + (double)fin[role * 4 + 3];
-    const double hi = fmax(v0, v1), lo = fmin(v0, v1);
-    const double lp2 = hi + log2(1.0 + exp2(fmax(lo - hi, -1000.0)));
-    d.logp2[role * d.B + b] = lp2;
-    if (role == 0) {
-      const float cost = (float)(-lp2 * kLn2);
-      d.costs[b] = cost;
-      if (!(fabsf(cost) < 3.0e38f)) atomicOr(d.flags, 1);
-    }
-  }
+  if (role == 0)
+    ctc_ab_run<P, 0>(d, um, b, r, nthreads_needed, nbar, mbar, stages, bnd, fin, frames_per_stage);
+  else
+    ctc_ab_run<P, 1>(d, um, b, r, nthreads_needed, nbar, mbar + kStages, stages + kStages * kStageFloats,
+                     bnd + 64, fin + 4, frames_per_stage);
 }
 
 // ===========================================================================
@@ -767,7 +786,10 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
 
   // K2 geometry: P pairs per thread so that one direction fits 512 threads
   const int npairs = p.maxL + 1;
-  const int P = npairs <= 512 ? 1 : (npairs <= 1024 ? 2 : 4);
+  // (measured: above ~8 warps per direction the frame loop is issue-bound and 2 pairs per thread win)
+  int P = npairs <= 256 ? 1 : (npairs <= 1024 ? 2 : 4);
+  static const int force_p = getenv("B200CTC_P") ? atoi(getenv("B200CTC_P")) : 0;   // tuning aid
+  if ((force_p == 2 || force_p == 4) && force_p > P) P = force_p;
   dev.P = P;
   // Launch K1 -> K2 -> K3 per utterance group.  With two groups on two streams the latency-bound
   // alpha/beta recursion of one group runs under the bandwidth-bound row kernels of the other.
