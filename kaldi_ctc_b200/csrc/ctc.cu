@@ -810,18 +810,26 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   const bool prof = getenv("B200CTC_PROFILE") != nullptr;
   // (only worth it when the row kernels are long: a slab of >= 256 MB)
   const bool big = (size_t)p.Tmax * B * A >= ((size_t)64 << 20);
-  const int ngroups = (B >= 16 && big && !prof && !getenv("B200CTC_ONE_STREAM")) ? 2 : 1;
-  static cudaStream_t side = nullptr;
-  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  if (ngroups == 2 && !side) {
-    if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)
+  // Utterance groups on separate streams: the latency-bound alpha/beta recursion of one group runs
+  // under the bandwidth-bound row kernels of the others (only the first K2 and the last K3 stay exposed).
+  constexpr int kMaxGroups = 8;
+  static const int env_groups = getenv("B200CTC_GROUPS") ? atoi(getenv("B200CTC_GROUPS")) : 0;
+  int ngroups = B >= 16 ? 2 : 1;   // measured at B=256, A=4000: 1 -> 10.47 ms, 2 -> 9.95, 4 -> 9.91, 8 -> 9.99
+  if (env_groups >= 1 && env_groups <= kMaxGroups) ngroups = std::min(env_groups, B);
+  if (!big || prof || getenv("B200CTC_ONE_STREAM")) ngroups = 1;
+  static cudaStream_t side[kMaxGroups] = {};
+  static cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {};
+  if (ngroups > 1 && !ev_fork &&
+      cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess)
+    return CTC_STATUS_EXECUTION_FAILED;
+  for (int gi = 1; gi < ngroups; gi++) {
+    if (!side[gi] && (cudaStreamCreateWithFlags(&side[gi], cudaStreamNonBlocking) != cudaSuccess ||
+                      cudaEventCreateWithFlags(&ev_join[gi], cudaEventDisableTiming) != cudaSuccess))
       return CTC_STATUS_EXECUTION_FAILED;
   }
-  if (ngroups == 2) {
+  if (ngroups > 1) {
     cudaEventRecord(ev_fork, stream);  // header copy + prior work of the caller's stream
-    cudaStreamWaitEvent(side, ev_fork, 0);
+    for (int gi = 1; gi < ngroups; gi++) cudaStreamWaitEvent(side[gi], ev_fork, 0);
   }
   cudaEvent_t ev[4];
   if (prof) {
@@ -829,9 +837,9 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
     cudaEventRecord(ev[0], stream);
   }
   for (int gi = 0; gi < ngroups; gi++) {
-    cudaStream_t st = gi == 0 ? stream : side;
-    dev.b_lo = gi == 0 ? 0 : B / 2;
-    dev.nb = ngroups == 1 ? B : (gi == 0 ? B / 2 : B - B / 2);
+    cudaStream_t st = gi == 0 ? stream : side[gi];
+    dev.b_lo = (int)((long long)B * gi / ngroups);
+    dev.nb = (int)((long long)B * (gi + 1) / ngroups) - dev.b_lo;
     const long long rows = (long long)p.Tmax * dev.nb;
     const unsigned g1 = (unsigned)((rows + kK1Warps - 1) / kK1Warps);
     ctc_rowstats_gather_kernel<<<g1, kK1Warps * 32, 0, st>>>(dev);
@@ -848,9 +856,9 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
       if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
     }
   }
-  if (ngroups == 2) {
-    cudaEventRecord(ev_join, side);
-    cudaStreamWaitEvent(stream, ev_join, 0);
+  for (int gi = 1; gi < ngroups; gi++) {
+    cudaEventRecord(ev_join[gi], side[gi]);
+    cudaStreamWaitEvent(stream, ev_join[gi], 0);
   }
   if (prof) {
     cudaEventRecord(ev[3], stream);
