@@ -155,11 +155,53 @@ def ctc_roofline(dev, pk, pk_src, B=256):
     costs = cd.cpu().numpy()
     nbytes = ctc.algorithmic_bytes(L, T, A)
     ach = nbytes / ms / 1e6
+    # what the three kernels must physically move: the slab is read twice (row statistics, then softmax
+    # for the gradient) and written once, plus the per-utterance alpha/beta/E tables written and read once
+    pitch = (L.astype(np.int64) + 1 + 3) // 4 * 4
+    tables = float((T.astype(np.int64) * pitch * 5 * 2 * 4).sum())
+    physical = 2.0 * 4 * A * float(T.sum()) + 4.0 * A * Tmax * B + tables
+    traffic, traffic_src = ncu_traffic("ctc_grad")
     return {"workload": "configs[4]: A=4000, B=%d, T_b~U{1500..3000}, L_b~U{50..600}, 1 GPU" % B, "bound": "hbm",
             "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-            "ms_per_call": ms, "algorithmic_bytes": int(nbytes), "peak_source": pk_src, "traffic": None,
+            "ms_per_call": ms, "algorithmic_bytes": int(nbytes), "peak_source": pk_src,
+            "physical_bytes_3_passes_plus_tables": int(physical), "physical_GBps": physical / ms / 1e6,
+            "physical_frac": physical / ms / 1e6 / pk["hbm_gbs"],
+            "traffic": traffic, "traffic_source": (traffic_src + " (ctc_grad_kernel, B=32 slice)") if traffic_src else None,
             "costs_finite": bool(np.isfinite(costs).all() and (costs > 0).all()),
             "l2": "inputs (12.3 GB) + outputs (12.3 GB) >> 126 MB L2"}
+
+
+def gemm_roofline(dev, pk, pk_src):
+    """The hoisted input projection of layers 2-5 (32000 x 1280 x 640, fp32 operands, TF32 tensor cores) timed
+    alone with CUDA events, L2 flushed between launches.  Peak: TF32 dense = half the measured bf16 rate."""
+    import torch
+    from kaldi_ctc_b200 import rnn
+    M, N, K = 32000, 1280, 640
+    A = torch.randn(M, K, device=dev)
+    Bm = torch.randn(N, K, device=dev)
+    C = torch.empty(M, N, device=dev)
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    run = lambda: rnn.gemm(torch, 0, 1, M, N, K, 1.0, A, K, Bm, K, 0.0, C, N, math=rnn.MATH_TENSOR, workspace=ws)
+    for _ in range(3):
+        run()
+    ts = []
+    for _ in range(10):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    ach = 2.0 * M * N * K / ms / 1e9
+    peak = pk.get("bf16_tflops", pk.get("bf16_tflops_sustained")) / 2.0
+    traffic, src = ncu_traffic("tc_gemm")
+    return {"kernel": "tc_gemm_kernel (x.Wi^T, %dx%dx%d)" % (M, N, K), "bound": "tensor", "achieved": ach,
+            "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "us_per_launch": ms * 1e3,
+            "peak_source": pk_src + " (bf16 burst / 2 = TF32 dense)", "traffic": traffic, "traffic_source": src,
+            "l2": "256 MB flush write between launches"}
 
 
 def ncu_traffic(kernel_substr):
@@ -300,6 +342,7 @@ def run_b200(args, rank, local_rank, world):
         del up
         torch.cuda.empty_cache()
         line["ctc_roofline"] = ctc_roofline(dev, pk, pk_src)
+        line["gemm_roofline"] = gemm_roofline(dev, pk, pk_src)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(spec, blobs, aw, ab)
