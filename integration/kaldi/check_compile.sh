@@ -15,4 +15,7 @@ for f in cudamatrix/cudnn-utils.cc cudamatrix/cudnn-recurrent.cc cudamatrix/cu-d
 done
 echo "checking ctc.h call-site shape"
 $CXX -std=c++11 -fsyntax-only -Wall -I"$ROOT/include" "$HERE/ctc_callsite_check.cc"
+echo "checking the nnet3 adapter (integration/kaldi/nnet3) against the reference's nnet3 headers"
+$CXX -std=c++11 -fsyntax-only -w -DHAVE_CUDA=1 -DHAVE_CLAPACK -DKALDI_DOUBLEPRECISION=0 -I"$ROOT/include" -I"$HERE/shim" \
+     -I"$HERE/nnet3" -I"$REF/src" -I"$REF/tools/CLAPACK" -I/usr/local/cuda/include "$HERE/nnet3/compile_check.cc"
 echo "OK: reference sources compile against the drop-in headers"
