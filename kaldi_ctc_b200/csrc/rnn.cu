@@ -384,7 +384,21 @@ b200rnnStatus_t b200rnnBackwardData(b200rnnPlan_t p, int T, const float *y, cons
       if (p->tcNC && !getenv("B200RNN_TC_NO_BWD")) {
         a.NC = p->tcNC; a.U = 32; a.BC = p->tcBC;
         a.bias_partial = rs + p->r_bias[l];
+        static long long *dbgb = nullptr;
+        const bool profb = getenv("B200RNN_TC_PROFILE") != nullptr;
+        if (profb && !dbgb) cudaMalloc(&dbgb, 64 * sizeof(long long));
+        if (profb) cudaMemsetAsync(dbgb, 0, 64 * sizeof(long long), stream);
+        a.dbg = profb ? dbgb : nullptr;
         CK(rec_tc_backward(a, stream));
+        if (profb) {  // tuning aid: cycles per step of each phase (cluster 0, CTA 0)
+          long long h[16];
+          cudaStreamSynchronize(stream);
+          cudaMemcpy(h, dbgb, sizeof(h), cudaMemcpyDeviceToHost);
+          const double n = T;
+          fprintf(stderr, "[b200rnn bwd tc] cyc/step epilogue: wait_recv %.0f sum %.0f math %.0f pack+fence+arrive %.0f "
+                  "gstore+prefetch %.0f wait_acc %.0f tmem_ld+st.async %.0f | mma warp: wait_dg %.0f fence+issue+commit %.0f\n",
+                  h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[8] / n, h[9] / n);
+        }
         p->tc_bwd_used = true;
       } else if (p->NC) {
         CK(rec_fp32_backward(a, stream));

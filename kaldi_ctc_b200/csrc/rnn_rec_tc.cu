@@ -485,8 +485,12 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
     const uint32_t dg0 = __shfl_sync(0xffffffffu, smem_u32(dgs), 0);
     const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint64_t bd0 = smem_desc(dg0, 0, 1024, kLayoutSw128);
+    const bool profm = a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == 1;
+    long long qm[3] = {0, 0, 0};
     for (int step = 0; step + 1 < T; step++) {
+      const long long n0 = profm ? clock64() : 0;
       mbar_wait(dg_ready, step & 1);
+      const long long n1 = profm ? clock64() : 0;
       tc_fence_after();
       for (int m = 1 - warp; m < MT; m += 2) {
 #pragma unroll
@@ -497,7 +501,12 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
       }
       if (elect_one()) tc_commit(acc_full);
       __syncwarp();
+      if (profm) {
+        const long long n2 = clock64();
+        qm[0] += n1 - n0; qm[1] += n2 - n1;
+      }
     }
+    if (profm && lane == 0) { a.dbg[8] = qm[0]; a.dbg[9] = qm[1]; }
   } else if (warp >= 2) {
     // ===================== epilogue =====================
     const int q = warp & 3;
@@ -506,6 +515,8 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
     const int unit = crank * UT + ul;
     float *gates = a.gates[dir];
     float *cell = a.cell[dir];
+    const bool prof = a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == 2;
+    long long pe[7] = {0, 0, 0, 0, 0, 0, 0};
     float carry[NJ];  // LSTM: dc carried to the previous step; GRU: dh * z
 #pragma unroll
     for (int j = 0; j < NJ; j++) carry[j] = 0.f;
@@ -559,17 +570,32 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
       float dhr[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; j++) dhr[j] = 0.f;
+      const long long c0 = prof ? clock64() : 0;
+      long long c1 = c0;
       if (step > 0) {
         const int use = p ? (step - 1) >> 1 : (step >> 1) - 1;
         mbar_wait(rfull + p, use & 1);
+        if (prof) c1 = clock64();
         // re-arm at once: the next fill of this buffer is two steps away
         if (warp == 2 && lane == 0) mbar_expect_tx(rfull + p, r_bytes);
-        const float *rc = recv + (size_t)p * recv_floats;
-        for (int src = 0; src < NC; src++) {
+        // all (<= 16) partial sums are loaded back to back, then added in a fixed pairwise order: a
+        // rolled loop of dependent load->add pairs cost 412 cycles per step here (measured)
+        const float *rc = recv + (size_t)p * recv_floats + ul * BC + s;
+        float t0[NJ], t1[NJ];
 #pragma unroll
-          for (int j = 0; j < NJ; j++) dhr[j] += rc[(src * 32 + ul) * BC + 4 * j + s];
+        for (int j = 0; j < NJ; j++) t0[j] = t1[j] = 0.f;
+#pragma unroll
+        for (int src = 0; src < 16; src += 2) {
+#pragma unroll
+          for (int j = 0; j < NJ; j++) {
+            if (src < NC) t0[j] += rc[src * 32 * BC + 4 * j];
+            if (src + 1 < NC) t1[j] += rc[(src + 1) * 32 * BC + 4 * j];
+          }
         }
+#pragma unroll
+        for (int j = 0; j < NJ; j++) dhr[j] = t0[j] + t1[j];
       }
+      const long long c2 = prof ? clock64() : 0;
       // ---- gate gradients of (unit, batch 4j+s)
       float dgv[NJ][4], dq[NJ];
 #pragma unroll
@@ -607,6 +633,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
         bsum[0] += dgv[j][0]; bsum[1] += dgv[j][1]; bsum[2] += dgv[j][2]; bsum[3] += dgv[j][3];
         bsq += dq[j];
       }
+      const long long c3 = prof ? clock64() : 0;
       if (step + 1 < T) {
         // ---- recurrent-side gradients -> BF16 B tile [utterance row][gate row r = 4*ul + g]
 #pragma unroll
@@ -620,6 +647,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
         fence_proxy_async();  // my generic smem writes -> visible to the tensor core (async proxy)
         mbar_arrive(dg_ready);
       }
+      const long long c4 = prof ? clock64() : 0;
       // ---- off the critical path: gradients to HBM, operands of the next step
 #pragma unroll
       for (int j = 0; j < NJ; j++) {
@@ -636,23 +664,34 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
       if (step + 1 < T) {
         // my (unit, batch) operands of the next step are not touched by anyone else: safe to prefetch now
         load_step(step + 1);
+        const long long c5 = prof ? clock64() : 0;
         // ---- partial dh_{prev} of my rows, for all k: scatter to the owners
         mbar_wait(acc_full, step & 1);
+        const long long c6 = prof ? clock64() : 0;
+        if (prof) { pe[0] += c1 - c0; pe[1] += c2 - c1; pe[2] += c3 - c2; pe[3] += c4 - c3; pe[4] += c5 - c4; pe[5] += c6 - c5; }
         tc_fence_after();
         const int pn = (step + 1) & 1;
-        for (int m = 0; m < MT; m++) {
-          uint32_t r[16];
-          tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + m * NPAD, r);
-          tmem_ld_wait();
-          if (4 * m + q < NC) {
+        // all tiles' loads in flight, ONE wait, then the stores (was a load->wait->store chain per tile)
+        uint32_t r[4][16];
+#pragma unroll
+        for (int m = 0; m < 4; m++)
+          if (m < MT) tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + m * NPAD, r[m]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          if (m < MT && 4 * m + q < NC) {
             const uint32_t dst = rdst[m] + (uint32_t)pn * r_bytes, bar = rbar[m] + pn * 8;
 #pragma unroll
-            for (int j = 0; j < NJ; j++) st_async_v4(dst + j * 16, r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3], bar);
+            for (int j = 0; j < NJ; j++)
+              st_async_v4(dst + j * 16, r[m][4 * j], r[m][4 * j + 1], r[m][4 * j + 2], r[m][4 * j + 3], bar);
           }
         }
         tc_fence_before();
+        if (prof) pe[6] += clock64() - c6;
       }
     }
+    if (prof && lane == 0)
+      for (int i = 0; i < 7; i++) a.dbg[i] = pe[i];
     // ---- bias gradients of this chunk: add the four utterance slots, slot 0 writes
     if (a.bias_partial) {
 #pragma unroll
