@@ -426,8 +426,8 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
   float *recv = reinterpret_cast<float *>(smem + 4096);            // [2][NC][32][BC]
   const int recv_floats = NC * 32 * BC;
   uint64_t *rfull = reinterpret_cast<uint64_t *>(smem + 4096 + 2 * recv_floats * 4);  // [2]
-  uint64_t *acc_full = rfull + 2;
-  uint64_t *dg_ready = acc_full + 1;
+  uint64_t *acc_full = rfull + 2;          // [4]: one per M tile, so a tile can leave while the next computes
+  uint64_t *dg_ready = acc_full + 4;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(dg_ready + 1);
   const uint32_t r_bytes = (uint32_t)recv_floats * 4u;  // bytes one step delivers into a receive buffer
 
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
   if (tid == 0) {
     mbar_init(rfull + 0, 1);
     mbar_init(rfull + 1, 1);
-    mbar_init(acc_full, 2);  // one commit from each issuing warp
+    for (int m = 0; m < 4; m++) mbar_init(acc_full + m, 1);  // committed by the warp that issued the tile
     mbar_init(dg_ready, 128);
     fence_barrier_init();
     mbar_expect_tx(rfull + 0, r_bytes);
@@ -498,8 +498,8 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
           const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * 2048 + (kk & 3) * 32) >> 4);
           if (elect_one()) mma_bf16_ts(tmem_d + m * NPAD, tmem_d + 64 + m * 64 + kk * 8, bd, idesc, kk ? 1u : 0u);
         }
+        if (elect_one()) tc_commit(acc_full + m);
       }
-      if (elect_one()) tc_commit(acc_full);
       __syncwarp();
       if (profm) {
         const long long n2 = clock64();
@@ -666,24 +666,27 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
         load_step(step + 1);
         const long long c5 = prof ? clock64() : 0;
         // ---- partial dh_{prev} of my rows, for all k: scatter to the owners
-        mbar_wait(acc_full, step & 1);
-        const long long c6 = prof ? clock64() : 0;
-        if (prof) { pe[0] += c1 - c0; pe[1] += c2 - c1; pe[2] += c3 - c2; pe[3] += c4 - c3; pe[4] += c5 - c4; pe[5] += c6 - c5; }
-        tc_fence_after();
         const int pn = (step + 1) & 1;
-        // all tiles' loads in flight, ONE wait, then the stores (was a load->wait->store chain per tile)
-        uint32_t r[4][16];
-#pragma unroll
-        for (int m = 0; m < 4; m++)
-          if (m < MT) tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + m * NPAD, r[m]);
-        tmem_ld_wait();
+        long long c6 = c5;
+        // tile by tile, in the order the tensor pipe finishes them (warp 1 issues tiles 0, 2; warp 0 tile 1):
+        // the partial sums of an early tile are in flight while the later tiles still compute
 #pragma unroll
         for (int m = 0; m < 4; m++) {
-          if (m < MT && 4 * m + q < NC) {
-            const uint32_t dst = rdst[m] + (uint32_t)pn * r_bytes, bar = rbar[m] + pn * 8;
+          if (m < MT) {
+            mbar_wait(acc_full + m, step & 1);
+            if (prof && m == 0) {
+              c6 = clock64();
+              pe[0] += c1 - c0; pe[1] += c2 - c1; pe[2] += c3 - c2; pe[3] += c4 - c3; pe[4] += c5 - c4; pe[5] += c6 - c5;
+            }
+            tc_fence_after();
+            uint32_t r[16];
+            tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + m * NPAD, r);
+            tmem_ld_wait();
+            if (4 * m + q < NC) {
+              const uint32_t dst = rdst[m] + (uint32_t)pn * r_bytes, bar = rbar[m] + pn * 8;
 #pragma unroll
-            for (int j = 0; j < NJ; j++)
-              st_async_v4(dst + j * 16, r[m][4 * j], r[m][4 * j + 1], r[m][4 * j + 2], r[m][4 * j + 3], bar);
+              for (int j = 0; j < NJ; j++) st_async_v4(dst + j * 16, r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3], bar);
+            }
           }
         }
         tc_fence_before();
@@ -779,7 +782,7 @@ cudaError_t launch_fwd(const RecArgs &a, cudaStream_t stream) {
 }
 
 size_t bwd_smem_bytes(int H, int BC) {
-  return std::max(kSmemFloor, 1024 + 4096 + (size_t)2 * (H / UT) * 32 * BC * 4 + 64);
+  return std::max(kSmemFloor, 1024 + 4096 + (size_t)2 * (H / UT) * 32 * BC * 4 + 128);
 }
 
 template <int MODE>
