@@ -252,14 +252,17 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
     // slot 3 carries the input part of n (slot 2 = recurrent part, nothing to load)
     const int pcol = MODE == 3 ? (s == 3 ? 2 : s) : s;
     const bool pload = MODE == 2 ? true : (MODE == 3 ? (s != 2) : (s == 0));
-    float pre[BC];
-    auto load_pre = [&](int step) {
+    // the hoisted projection is prefetched TWO steps ahead into ping-pong registers: with one step of
+    // distance the per-step time grew from 0.92 us (T = 250, rows still in L2) to 1.03 us (T = 2000, HBM)
+    float preA[BC], preB[BC];
+    auto load_pre = [&](float (&dst)[BC], int step) {
       const int t = dir ? T - 1 - step : step;
       const float *pp = gates + ((size_t)t * B + b_lo) * GH + (size_t)pcol * H + unit;
 #pragma unroll
-      for (int b = 0; b < BC; b++) pre[b] = (pload && b < nb) ? pp[(size_t)b * GH] : 0.f;
+      for (int b = 0; b < BC; b++) dst[b] = (pload && b < nb) ? pp[(size_t)b * GH] : 0.f;
     };
-    load_pre(0);
+    load_pre(preA, 0);
+    if (T > 1) load_pre(preB, 1);
 
     // remote addresses that never change
     const int kb_mine = crank >> 1, chunk_mine = (crank & 1) * 4 + q;
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
 
     const bool prof = a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == 2;
     long long pe[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int step = 0; step < T; step++) {
+    auto do_step = [&](const int step, float (&pre)[BC]) {
       const int t = dir ? T - 1 - step : step;
       const long long c0 = prof ? clock64() : 0;
       asm volatile("bar.sync 2, 160;" ::: "memory");
@@ -373,13 +376,17 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
           }
         }
       }
-      if (step + 1 < T) load_pre(step + 1);
+      if (step + 2 < T) load_pre(pre, step + 2);   // this step's registers are free again
       if (prof) {
         const long long c7 = clock64();
         if (lane == 0) { a.dbg[13] += c1; a.dbg[15] += c4; }      // accumulator seen by the epilogue / h sent
         pe[0] += c1 - c0; pe[1] += c2 - c1; pe[2] += c3 - c2; pe[3] += c4 - c3;
         pe[4] += c5 - c4; pe[5] += c6 - c5; pe[6] += c7 - c6;
       }
+    };
+    for (int step = 0; step < T; step += 2) {
+      do_step(step, preA);
+      if (step + 1 < T) do_step(step + 1, preB);
     }
     if (prof && lane == 0)
       for (int i = 0; i < 7; i++) a.dbg[i] = pe[i];
