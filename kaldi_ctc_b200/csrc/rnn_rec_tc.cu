@@ -529,9 +529,16 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
     for (int j = 0; j < NJ; j++) carry[j] = 0.f;
     float bsum[4] = {0.f, 0.f, 0.f, 0.f}, bsq = 0.f;  // bias gradients: sums over time and my utterances
 
-    // operands of the step, prefetched one step ahead
-    float pdy[NJ], pg[NJ][G], pc[NJ], pcp[NJ];
-    auto load_step = [&](int step) {
+    // operands of the step, prefetched two steps ahead into ping-pong registers
+    struct Ops {
+      float dy[NJ], g[NJ][G], c[NJ], cp[NJ];
+    };
+    Ops opsA, opsB;
+    auto load_step = [&](Ops &o, int step) {
+      float (&pdy)[NJ] = o.dy;
+      float (&pg)[NJ][G] = o.g;
+      float (&pc)[NJ] = o.c;
+      float (&pcp)[NJ] = o.cp;
       const int fstep = T - 1 - step;
       const int t = dir ? T - 1 - fstep : fstep;
       const int tp = dir ? t + 1 : t - 1;
@@ -556,7 +563,8 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
         }
       }
     };
-    load_step(0);
+    load_step(opsA, 0);
+    if (T > 1) load_step(opsB, 1);
 
     // destination of my TMEM lanes' partial sums: for tile m, lanes of this warp are the 32
     // units of CTA 4m+q; inside its receive buffer: [parity][src = crank][lane][b]
@@ -569,7 +577,11 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
       rbar[m] = mapa_u32(smem_u32(rfull), ok ? tgt : 0);
     }
 
-    for (int step = 0; step < T; step++) {
+    auto do_step = [&](const int step, Ops &ops) {
+      float (&pdy)[NJ] = ops.dy;
+      float (&pg)[NJ][G] = ops.g;
+      float (&pc)[NJ] = ops.c;
+      float (&pcp)[NJ] = ops.cp;
       const int fstep = T - 1 - step;
       const int t = dir ? T - 1 - fstep : fstep;
       const int p = step & 1;
@@ -588,19 +600,17 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
         // all (<= 16) partial sums are loaded back to back, then added in a fixed pairwise order: a
         // rolled loop of dependent load->add pairs cost 412 cycles per step here (measured)
         const float *rc = recv + (size_t)p * recv_floats + ul * BC + s;
-        float t0[NJ], t1[NJ];
 #pragma unroll
-        for (int j = 0; j < NJ; j++) t0[j] = t1[j] = 0.f;
+        for (int j = 0; j < NJ; j++) {
+          float v[16];
 #pragma unroll
-        for (int src = 0; src < 16; src += 2) {
+          for (int src = 0; src < 16; src++) v[src] = src < NC ? rc[src * 32 * BC + 4 * j] : 0.f;  // 16 loads in flight
 #pragma unroll
-          for (int j = 0; j < NJ; j++) {
-            if (src < NC) t0[j] += rc[src * 32 * BC + 4 * j];
-            if (src + 1 < NC) t1[j] += rc[(src + 1) * 32 * BC + 4 * j];
-          }
+          for (int w2 = 8; w2 >= 1; w2 >>= 1)   // fixed-order tree: deterministic
+#pragma unroll
+            for (int i = 0; i < w2; i++) v[i] += v[i + w2];
+          dhr[j] = v[0];
         }
-#pragma unroll
-        for (int j = 0; j < NJ; j++) dhr[j] = t0[j] + t1[j];
       }
       const long long c2 = prof ? clock64() : 0;
       // ---- gate gradients of (unit, batch 4j+s)
@@ -669,8 +679,8 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
         }
       }
       if (step + 1 < T) {
-        // my (unit, batch) operands of the next step are not touched by anyone else: safe to prefetch now
-        load_step(step + 1);
+        // my (unit, batch) operands of later steps are not touched by anyone else: safe to prefetch now
+        if (step + 2 < T) load_step(ops, step + 2);
         const long long c5 = prof ? clock64() : 0;
         // ---- partial dh_{prev} of my rows, for all k: scatter to the owners
         const int pn = (step + 1) & 1;
@@ -699,6 +709,10 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
         tc_fence_before();
         if (prof) pe[6] += clock64() - c6;
       }
+    };
+    for (int step = 0; step < T; step += 2) {
+      do_step(step, opsA);
+      if (step + 1 < T) do_step(step + 1, opsB);
     }
     if (prof && lane == 0)
       for (int i = 0; i < 7; i++) a.dbg[i] = pe[i];
