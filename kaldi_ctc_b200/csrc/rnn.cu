@@ -326,6 +326,7 @@ b200rnnStatus_t b200rnnForward(b200rnnPlan_t p, int T, const float *x, const flo
         if (prof && !dbg) cudaMalloc(&dbg, 64 * sizeof(long long));
         if (prof) cudaMemsetAsync(dbg, 0, 64 * sizeof(long long), stream);
         a.dbg = prof ? dbg : nullptr;
+        a.dbg_flags = getenv("B200RNN_TC_DBG") ? atoi(getenv("B200RNN_TC_DBG")) : 0;
         CK(rec_tc_forward(a, stream));
         if (prof) {  // tuning aid: cycles per step of each phase (cluster 0, CTA 0)
           long long h[24];

@@ -42,6 +42,7 @@ constexpr int UT = 32;          // hidden units per CTA
 constexpr int NPAD = 16;        // MMA N (utterances per chunk, zero padded)
 constexpr int kThreads = 192;   // warps 0,1: MMA issuers (one accumulator each), warps 2-5: epilogue
 constexpr int kTmemCols = 256;  // D: columns [0,16); A (R slice): columns [32, 32 + H/2)
+constexpr int kRingOffset = 48 * 1024;   // forward kernel: cp.async prefetch ring (32 KB) behind the h tiles + barriers
 constexpr int kACol = 32;       // (several independent accumulators were measured: no gain, the
                                 //  burst is issue-bound at ~24 cycles per MMA, tools/mma_bench.cu)
 
@@ -252,17 +253,30 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
     // slot 3 carries the input part of n (slot 2 = recurrent part, nothing to load)
     const int pcol = MODE == 3 ? (s == 3 ? 2 : s) : s;
     const bool pload = MODE == 2 ? true : (MODE == 3 ? (s != 2) : (s == 0));
-    // the hoisted projection is prefetched TWO steps ahead into ping-pong registers: with one step of
-    // distance the per-step time grew from 0.92 us (T = 250, rows still in L2) to 1.03 us (T = 2000, HBM)
-    float preA[BC], preB[BC];
-    auto load_pre = [&](float (&dst)[BC], int step) {
-      const int t = dir ? T - 1 - step : step;
-      const float *pp = gates + ((size_t)t * B + b_lo) * GH + (size_t)pcol * H + unit;
+    // The hoisted projection rows are prefetched kPF steps ahead with cp.async into a per-thread ring in
+    // shared memory (each thread only ever reads what it copied itself, so cp.async.wait_group is the only
+    // synchronisation).  Register prefetch one step ahead cost 12 % of the step at T = 2000 (HBM latency
+    // tails of the slowest thread of the slowest CTA gate every step); 2 / 4 steps ahead recovered 11 / 15 %.
+    constexpr int kPF = BC == 4 ? 16 : (BC == 8 ? 8 : 4);
+    float *pring = reinterpret_cast<float *>(smem + kRingOffset) + (size_t)(tid - 64) * BC;   // + slot * 128 * BC
+    auto issue_pre = [&](int step) {
+      if (step < T && pload && !(a.dbg_flags & 2)) {
+        const int t = dir ? T - 1 - step : step;
+        const float *pp = gates + ((size_t)t * B + b_lo) * GH + (size_t)pcol * H + unit;
+        const uint32_t dst = smem_u32(pring + (size_t)(step % kPF) * 128 * BC);
 #pragma unroll
-      for (int b = 0; b < BC; b++) dst[b] = (pload && b < nb) ? pp[(size_t)b * GH] : 0.f;
+        for (int b = 0; b < BC; b++)
+          if (b < nb)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4 * b), "l"(pp + (size_t)b * GH) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    load_pre(preA, 0);
-    if (T > 1) load_pre(preB, 1);
+#pragma unroll
+    for (int k = 0; k < kPF; k++) {   // slots of (thread, b) pairs that are never copied stay zero
+#pragma unroll
+      for (int b = 0; b < BC; b++) pring[(size_t)k * 128 * BC + b] = 0.f;
+    }
+    for (int k = 0; k < kPF; k++) issue_pre(k);
 
     // remote addresses that never change
     const int kb_mine = crank >> 1, chunk_mine = (crank & 1) * 4 + q;
@@ -275,12 +289,20 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
 
     const bool prof = a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == 2;
     long long pe[7] = {0, 0, 0, 0, 0, 0, 0};
-    auto do_step = [&](const int step, float (&pre)[BC]) {
+    for (int step = 0; step < T; step++) {
       const int t = dir ? T - 1 - step : step;
       const long long c0 = prof ? clock64() : 0;
+      // this step's projection rows (copied kPF steps ago)
+      asm volatile("cp.async.wait_group %0;" ::"n"(kPF - 1) : "memory");
+      float pre[BC];
+      {
+        const float *ps = pring + (size_t)(step % kPF) * 128 * BC;
+#pragma unroll
+        for (int b = 0; b < BC; b++) pre[b] = ps[b];
+      }
       asm volatile("bar.sync 2, 160;" ::: "memory");
       const long long c1a = prof ? clock64() : 0;
-      tc_fence_after();
+      if (!(a.dbg_flags & 4)) tc_fence_after();
       const long long c1 = prof ? clock64() : 0;
       if (prof && lane == 0) a.dbg[16] += c1 - c1a;
       uint32_t ra[32];
@@ -364,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
 #pragma unroll
       for (int j = 0; j < NJ; j++) {
         const int b = 4 * j + s;
-        if (b < nb) {
+        if (b < nb && !(a.dbg_flags & 1)) {
           const size_t row = (size_t)t * B + b_lo + b;
           a.y[row * HO + dir * H + unit] = hnew[j];
           if (a.save) {
@@ -376,17 +398,13 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
           }
         }
       }
-      if (step + 2 < T) load_pre(pre, step + 2);   // this step's registers are free again
+      issue_pre(step + kPF);   // refills the slot this step has just consumed
       if (prof) {
         const long long c7 = clock64();
         if (lane == 0) { a.dbg[13] += c1; a.dbg[15] += c4; }      // accumulator seen by the epilogue / h sent
         pe[0] += c1 - c0; pe[1] += c2 - c1; pe[2] += c3 - c2; pe[3] += c4 - c3;
         pe[4] += c5 - c4; pe[5] += c6 - c5; pe[6] += c7 - c6;
       }
-    };
-    for (int step = 0; step < T; step += 2) {
-      do_step(step, preA);
-      if (step + 1 < T) do_step(step + 1, preB);
     }
     if (prof && lane == 0)
       for (int i = 0; i < 7; i++) a.dbg[i] = pe[i];
@@ -783,7 +801,7 @@ cudaError_t launch_cluster(K kernel, const RecArgs &a, size_t smem, cudaStream_t
 
 // >= 116 KB so that two CTAs never share an SM (each owns 256+ TMEM columns and an issue slot)
 constexpr size_t kSmemFloor = 116 * 1024;
-size_t fwd_smem_bytes(int H) { return std::max(kSmemFloor, 1024 + (size_t)(H / 64) * (2 * 2048) + 64); }
+size_t fwd_smem_bytes(int H) { return std::max(kSmemFloor, 1024 + (size_t)kRingOffset + 32 * 1024); }
 
 template <int MODE>
 cudaError_t launch_fwd(const RecArgs &a, cudaStream_t stream) {
