@@ -547,11 +547,12 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
     for (int j = 0; j < NJ; j++) carry[j] = 0.f;
     float bsum[4] = {0.f, 0.f, 0.f, 0.f}, bsq = 0.f;  // bias gradients: sums over time and my utterances
 
-    // operands of the step, prefetched two steps ahead into ping-pong registers
+    // operands of the step, prefetched kD steps ahead into rotating registers
     struct Ops {
       float dy[NJ], g[NJ][G], c[NJ], cp[NJ];
     };
-    Ops opsA, opsB;
+    constexpr int kD = NJ == 1 ? 4 : 2;   // prefetch distance in steps (registers: 7 * NJ per step in flight)
+    Ops opsR[kD];
     auto load_step = [&](Ops &o, int step) {
       float (&pdy)[NJ] = o.dy;
       float (&pg)[NJ][G] = o.g;
@@ -581,8 +582,9 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
         }
       }
     };
-    load_step(opsA, 0);
-    if (T > 1) load_step(opsB, 1);
+#pragma unroll
+    for (int i = 0; i < kD; i++)
+      if (i < T) load_step(opsR[i], i);
 
     // destination of my TMEM lanes' partial sums: for tile m, lanes of this warp are the 32
     // units of CTA 4m+q; inside its receive buffer: [parity][src = crank][lane][b]
@@ -698,7 +700,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
       }
       if (step + 1 < T) {
         // my (unit, batch) operands of later steps are not touched by anyone else: safe to prefetch now
-        if (step + 2 < T) load_step(ops, step + 2);
+        if (step + kD < T) load_step(ops, step + kD);
         const long long c5 = prof ? clock64() : 0;
         // ---- partial dh_{prev} of my rows, for all k: scatter to the owners
         const int pn = (step + 1) & 1;
@@ -728,9 +730,10 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
         if (prof) pe[6] += clock64() - c6;
       }
     };
-    for (int step = 0; step < T; step += 2) {
-      do_step(step, opsA);
-      if (step + 1 < T) do_step(step + 1, opsB);
+    for (int step = 0; step < T; step += kD) {
+#pragma unroll
+      for (int i = 0; i < kD; i++)
+        if (step + i < T) do_step(step + i, opsR[i]);
     }
     if (prof && lane == 0)
       for (int i = 0; i < 7; i++) a.dbg[i] = pe[i];
