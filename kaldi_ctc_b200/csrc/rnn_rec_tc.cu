@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
     struct Ops {
       float dy[NJ], g[NJ][G], c[NJ], cp[NJ];
     };
-    constexpr int kD = NJ == 1 ? 4 : 2;   // prefetch distance in steps (registers: 7 * NJ per step in flight)
+    constexpr int kD = NJ == 1 ? 8 : 2;   // prefetch distance in steps (registers: 7 * NJ per step in flight)
     Ops opsR[kD];
     auto load_step = [&](Ops &o, int step) {
       float (&pdy)[NJ] = o.dy;
