@@ -340,6 +340,11 @@ b200rnnStatus_t b200rnnForward(b200rnnPlan_t p, int T, const float *x, const flo
           fprintf(stderr, "[b200rnn fwd tc] issuer-complete -> epilogue-sees-acc %.0f cyc; h sent -> next h seen by issuer %.0f cyc\n",
                   (h[13] - h[12]) / n, (h[14] - h[15]) / n + (double)(h[8] + h[9] + h[10] + h[11]) / n);
           fprintf(stderr, "[b200rnn fwd tc] tcgen05.fence::after_thread_sync in the epilogue: %.0f cyc\n", h[16] / n);
+          long long hc[64];
+          cudaMemcpy(hc, dbg, sizeof(hc), cudaMemcpyDeviceToHost);
+          fprintf(stderr, "[b200rnn fwd tc] loop cycles/step per cluster (CTA 0):");
+          for (int c = 0; c < 8; c++) fprintf(stderr, " %.0f", hc[32 + c] / n);
+          fprintf(stderr, "\n");
         }
       } else if (p->NC) {
         CK(rec_fp32_forward(a, stream));

@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
 
     const bool prof = a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == 2;
     long long pe[7] = {0, 0, 0, 0, 0, 0, 0};
+    const long long loop_t0 = a.dbg ? clock64() : 0;
     for (int step = 0; step < T; step++) {
       const int t = dir ? T - 1 - step : step;
       const long long c0 = prof ? clock64() : 0;
@@ -408,6 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
     }
     if (prof && lane == 0)
       for (int i = 0; i < 7; i++) a.dbg[i] = pe[i];
+    if (a.dbg && warp == 2 && lane == 0 && blockIdx.y < 16) a.dbg[32 + blockIdx.y + 16 * (crank != 0)] = clock64() - loop_t0;
   }
   tc_fence_before();
   __syncthreads();
