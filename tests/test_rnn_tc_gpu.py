@@ -87,7 +87,9 @@ def _run_tc(mode, D, H, B, Tn, x, w, dy):
 
 
 @pytest.mark.parametrize("mode,D,H,B,Tn", [(2, 40, 320, 16, 40), (2, 640, 320, 16, 12), (3, 40, 320, 64, 25),
-                                          (2, 24, 64, 5, 30), (3, 24, 128, 17, 20), (2, 40, 320, 3, 200)])
+                                          (2, 24, 64, 5, 30), (3, 24, 128, 17, 20), (2, 40, 320, 3, 200),
+                                          (2, 40, 320, 32, 20),   # batch chunk 8 (two utterance slots per thread)
+                                          (3, 24, 64, 4, 3), (2, 24, 64, 4, 1)])   # T below the prefetch depth
 def test_tensor_mode_within_stated_tolerance(mode, D, H, B, Tn):
     from oracle import pyoracle
     rng = np.random.default_rng(mode * 100 + B + H)
