@@ -306,13 +306,15 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
       if (!(a.dbg_flags & 4)) tc_fence_after();
       const long long c1 = prof ? clock64() : 0;
       if (prof && lane == 0) a.dbg[16] += c1 - c1a;
-      uint32_t ra[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16), ra);
+      // only the BC columns of each issuer's accumulator that this chunk uses (TMEM reads are paced by bytes)
+      uint32_t ra0[BC], ra1[BC];
+      tmem_ld_32xN<BC>(tmem_base + ((uint32_t)(q * 32) << 16), ra0);
+      tmem_ld_32xN<BC>(tmem_base + ((uint32_t)(q * 32) << 16) + NPAD, ra1);
       tmem_ld_wait();
       tc_fence_before();
       float r[BC];  // the two issuers' partial sums
 #pragma unroll
-      for (int e = 0; e < BC; e++) r[e] = __uint_as_float(ra[e]) + __uint_as_float(ra[NPAD + e]);
+      for (int e = 0; e < BC; e++) r[e] = __uint_as_float(ra0[e]) + __uint_as_float(ra1[e]);
       const long long c2 = prof ? clock64() : 0;
 
       // ---- gates -> (unit, batch) threads, cell update; results kept in registers
@@ -718,8 +720,8 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
               pe[0] += c1 - c0; pe[1] += c2 - c1; pe[2] += c3 - c2; pe[3] += c4 - c3; pe[4] += c5 - c4; pe[5] += c6 - c5;
             }
             tc_fence_after();
-            uint32_t r[16];
-            tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + m * NPAD, r);
+            uint32_t r[BC];
+            tmem_ld_32xN<BC>(tmem_base + ((uint32_t)(q * 32) << 16) + m * NPAD, r);
             tmem_ld_wait();
             if (4 * m + q < NC) {
               const uint32_t dst = rdst[m] + (uint32_t)pn * r_bytes, bar = rbar[m] + pn * 8;
