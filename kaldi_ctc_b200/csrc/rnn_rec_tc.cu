@@ -40,10 +40,13 @@ using namespace tc;
 
 constexpr int UT = 32;          // hidden units per CTA
 constexpr int NPAD = 16;        // MMA N (utterances per chunk, zero padded)
-constexpr int kThreads = 192;   // warps 0,1: MMA issuers (one accumulator each), warps 2-5: epilogue
-constexpr int kTmemCols = 256;  // D: columns [0,16); A (R slice): columns [32, 32 + H/2)
+constexpr int kIssuers = 4;     // MMA-issuing warps: the burst of small MMAs is bound by the ~13 instructions ptxas
+                                // emits around every tcgen05.mma (tools/mma_bench.cu: 20 MMAs in 1135 / 855 / 480 cycles
+                                // with 1 / 2 / 4 issuing warps), so four warps issue a quarter of the K slices each
+constexpr int kThreads = 32 * kIssuers + 128;   // warps 0-3: MMA issuers (one accumulator each), warps 4-7: epilogue
+constexpr int kTmemCols = 256;  // D: columns [0,64) (four accumulators); A (R slice): columns [64, 64 + H/2)
 constexpr int kRingOffset = 48 * 1024;   // forward kernel: cp.async prefetch ring (32 KB) behind the h tiles + barriers
-constexpr int kACol = 32;       // (several independent accumulators were measured: no gain, the
+constexpr int kACol = 64;       // (several independent accumulators were measured: no gain, the
                                 //  burst is issue-bound at ~24 cycles per MMA, tools/mma_bench.cu)
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -137,14 +140,15 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
   if (tid == 0) {
     mbar_init(hfull + 0, 1);
     mbar_init(hfull + 1, 1);
-    mbar_init(acc_full, 2);  // one commit from each of the two issuing warps
+    mbar_init(acc_full, kIssuers);  // one commit from each issuing warp
     fence_barrier_init();
     // arm both h tiles for their first fill (st.async completes bytes on them)
     mbar_expect_tx(hfull + 0, h_bytes);
     mbar_expect_tx(hfull + 1, h_bytes);
   }
+  const uint32_t tmem_cols = kACol + H / 2 <= kTmemCols ? (uint32_t)kTmemCols : 512u;
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
   fence_proxy_async_all();  // zeroed h tiles -> visible to the tensor core (async proxy)
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // ---- one-time: my 128 gate rows of R -> BF16 -> tensor memory (lane = row, column = k/2)
-  if (warp >= 2) {
+  if (warp >= kIssuers) {
     const int q = warp & 3, row = q * 32 + lane;
     const int u = row >> 2, g = row & 3;
     const float *src = a.w_rec[dir] + ((size_t)(g < G ? g : 0) * H + crank * UT + u) * H;
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
   tc_fence_after();
   cluster.sync();  // every CTA's tiles and barriers exist before anyone writes remotely
 
-  if (warp < 2) {
+  if (warp < kIssuers) {
     // ===================== MMA issuers =====================
     // The burst of H/16 small MMAs is issue-bound (~30 cycles each), so two warps issue half of
     // the K range each into their own accumulator (columns [16*warp, 16*warp+16)); the epilogue
@@ -205,14 +209,14 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
         const uint32_t dacc = tmem_d + warp * NPAD;
         if (NKB > 0) {
 #pragma unroll
-          for (int i = 0; i < NKB * 2; i++) {
-            const int kk = 2 * i + warp;  // even K slices: warp 0, odd: warp 1
+          for (int i = 0; i < NKB; i++) {
+            const int kk = kIssuers * i + warp;  // K slices interleaved over the issuing warps
             const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * 2048 + (kk & 3) * 32) >> 4);
             if (elect_one()) mma_bf16_ts(dacc, tmem_d + kACol + kk * 8, bd, idesc, i ? 1u : 0u);
           }
         } else {
-          for (int i = 0; i < nkb * 2; i++) {
-            const int kk = 2 * i + warp;
+          for (int i = 0; i < nkb; i++) {
+            const int kk = kIssuers * i + warp;
             const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * 2048 + (kk & 3) * 32) >> 4);
             if (elect_one()) mma_bf16_ts(dacc, tmem_d + kACol + kk * 8, bd, idesc, i ? 1u : 0u);
           }
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
       }
     }
     if (prof && lane == 0) { a.dbg[8] = pm[0]; a.dbg[9] = pm[1]; a.dbg[10] = pm[2]; a.dbg[11] = pm[3]; }
-  } else if (warp >= 2) {
+  } else {
     // ===================== epilogue =====================
     const int q = warp & 3;                  // TMEM lane quarter
     const int s = lane & 3;                  // gate slot of my row / batch slot after the transpose
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
     // synchronisation).  Register prefetch one step ahead cost 12 % of the step at T = 2000 (HBM latency
     // tails of the slowest thread of the slowest CTA gate every step); 2 / 4 steps ahead recovered 11 / 15 %.
     constexpr int kPF = BC == 4 ? 16 : (BC == 8 ? 8 : 4);
-    float *pring = reinterpret_cast<float *>(smem + kRingOffset) + (size_t)(tid - 64) * BC;   // + slot * 128 * BC
+    float *pring = reinterpret_cast<float *>(smem + kRingOffset) + (size_t)(tid - 32 * kIssuers) * BC;   // + slot * 128 * BC
     auto issue_pre = [&](int step) {
       if (step < T && pload && !(a.dbg_flags & 2)) {
         const int t = dir ? T - 1 - step : step;
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
     const uint32_t rhf_a = mapa_u32(smem_u32(hfull), peer_a < NC ? peer_a : 0);
     const uint32_t rhf_b = mapa_u32(smem_u32(hfull), peer_b < NC ? peer_b : 0);
 
-    const bool prof = a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == 2;
+    const bool prof = a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == kIssuers;
     long long pe[7] = {0, 0, 0, 0, 0, 0, 0};
     const long long loop_t0 = a.dbg ? clock64() : 0;
     for (int step = 0; step < T; step++) {
@@ -307,14 +311,15 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
       const long long c1 = prof ? clock64() : 0;
       if (prof && lane == 0) a.dbg[16] += c1 - c1a;
       // only the BC columns of each issuer's accumulator that this chunk uses (TMEM reads are paced by bytes)
-      uint32_t ra0[BC], ra1[BC];
-      tmem_ld_32xN<BC>(tmem_base + ((uint32_t)(q * 32) << 16), ra0);
-      tmem_ld_32xN<BC>(tmem_base + ((uint32_t)(q * 32) << 16) + NPAD, ra1);
+      uint32_t ra[kIssuers][BC];
+#pragma unroll
+      for (int w = 0; w < kIssuers; w++) tmem_ld_32xN<BC>(tmem_base + ((uint32_t)(q * 32) << 16) + w * NPAD, ra[w]);
       tmem_ld_wait();
       tc_fence_before();
-      float r[BC];  // the two issuers' partial sums
+      float r[BC];  // the issuers' partial sums, added in a fixed order
 #pragma unroll
-      for (int e = 0; e < BC; e++) r[e] = __uint_as_float(ra0[e]) + __uint_as_float(ra1[e]);
+      for (int e = 0; e < BC; e++)
+        r[e] = (__uint_as_float(ra[0][e]) + __uint_as_float(ra[1][e])) + (__uint_as_float(ra[2][e]) + __uint_as_float(ra[3][e]));
       const long long c2 = prof ? clock64() : 0;
 
       // ---- gates -> (unit, batch) threads, cell update; results kept in registers
@@ -411,14 +416,14 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
     }
     if (prof && lane == 0)
       for (int i = 0; i < 7; i++) a.dbg[i] = pe[i];
-    if (a.dbg && warp == 2 && lane == 0 && blockIdx.y < 16) a.dbg[32 + blockIdx.y + 16 * (crank != 0)] = clock64() - loop_t0;
+    if (a.dbg && warp == kIssuers && lane == 0 && blockIdx.y < 16) a.dbg[32 + blockIdx.y + 16 * (crank != 0)] = clock64() - loop_t0;
   }
   tc_fence_before();
   __syncthreads();
   cluster.sync();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -480,7 +485,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // ---- one-time: R_slice^T -> BF16 -> tensor memory.  lane = k within the tile, column c = rows 2c, 2c+1
-  if (warp >= 2) {
+  if (warp >= kIssuers) {
     const int q = warp & 3;
     const float *Rg = a.w_rec[dir];
     for (int m = 0; m < MT; m++) {
@@ -508,8 +513,8 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
   tc_fence_after();
   cluster.sync();
 
-  if (warp < 2) {
-    // ===================== MMA issuers: warp 1 -> M-tiles 0, 2, ...; warp 0 -> tiles 1, 3 =====================
+  if (warp < kIssuers) {
+    // ===================== MMA issuers: warp w -> M tile w (MT <= 4) =====================
     constexpr uint32_t idesc = instr_desc(kFmtBF16, 0, 0, 128, NPAD);
     const uint32_t dg0 = __shfl_sync(0xffffffffu, smem_u32(dgs), 0);
     const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -521,7 +526,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
       mbar_wait(dg_ready, step & 1);
       const long long n1 = profm ? clock64() : 0;
       tc_fence_after();
-      for (int m = 1 - warp; m < MT; m += 2) {
+      for (int m = warp; m < MT; m += kIssuers) {
 #pragma unroll
         for (int kk = 0; kk < 8; kk++) {
           const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * 2048 + (kk & 3) * 32) >> 4);
@@ -536,7 +541,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
       }
     }
     if (profm && lane == 0) { a.dbg[8] = qm[0]; a.dbg[9] = qm[1]; }
-  } else if (warp >= 2) {
+  } else {
     // ===================== epilogue =====================
     const int q = warp & 3;
     const int s = lane & 3;
@@ -544,7 +549,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
     const int unit = crank * UT + ul;
     float *gates = a.gates[dir];
     float *cell = a.cell[dir];
-    const bool prof = a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == 2;
+    const bool prof = a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == kIssuers;
     long long pe[7] = {0, 0, 0, 0, 0, 0, 0};
     float carry[NJ];  // LSTM: dc carried to the previous step; GRU: dh * z
 #pragma unroll
@@ -620,7 +625,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
         mbar_wait(rfull + p, use & 1);
         if (prof) c1 = clock64();
         // re-arm at once: the next fill of this buffer is two steps away
-        if (warp == 2 && lane == 0) mbar_expect_tx(rfull + p, r_bytes);
+        if (warp == kIssuers && lane == 0) mbar_expect_tx(rfull + p, r_bytes);
         // all (<= 16) partial sums are loaded back to back, then added in a fixed pairwise order: a
         // rolled loop of dependent load->add pairs cost 412 cycles per step here (measured)
         const float *rc = recv + (size_t)p * recv_floats + ul * BC + s;
@@ -709,7 +714,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
         // ---- partial dh_{prev} of my rows, for all k: scatter to the owners
         const int pn = (step + 1) & 1;
         long long c6 = c5;
-        // tile by tile, in the order the tensor pipe finishes them (warp 1 issues tiles 0, 2; warp 0 tile 1):
+        // tile by tile (each issued and committed by its own warp):
         // the partial sums of an early tile are in flight while the later tiles still compute
 #pragma unroll
         for (int m = 0; m < 4; m++) {
@@ -847,7 +852,7 @@ cudaError_t launch_bwd(const RecArgs &a, cudaStream_t stream) {
 // and at most 16 CTAs of 32 units per cluster.
 bool rec_tc_supported(int mode, int H) {
   (void)mode;
-  return H % 64 == 0 && H / UT <= 16 && kACol + H / 2 <= kTmemCols;
+  return H % 64 == 0 && H / UT <= 16 && kACol + H / 2 <= 512;
 }
 
 // batch chunk: the smallest of {4, 8, 16} that keeps all clusters resident at once

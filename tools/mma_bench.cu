@@ -45,6 +45,56 @@ __global__ void __launch_bounds__(128, 1) k(long long *out, int nmma, int reps) 
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tm, 512); }
 }
 
+// NW issuing warps, each with its own accumulator and its own share of the 20 K slices (TS mode, N = 16):
+// is the burst bound by the tensor pipe or by the ~13 instructions ptxas emits around every tcgen05.mma?
+template <int NW>
+__global__ void __launch_bounds__(128, 1) kmw(long long *out, int nmma, int reps) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar, NW); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+  asm volatile("fence.proxy.async;" ::: "memory");
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tm = __shfl_sync(0xffffffffu, slot, 0);
+  if (warp < NW) {
+    constexpr uint32_t idesc = instr_desc(kFmtBF16, 0, 0, 128, 16);
+    const uint32_t b0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0) + 32768;
+    long long tot = 0;
+    for (int r = 0; r < reps; r++) {
+      asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+      const long long t0 = clock64();
+      int first = 1;
+      for (int kk = warp; kk < nmma; kk += NW) {
+        const uint64_t bd = smem_desc(b0 + (kk & 3) * 32, 0, 1024, kLayoutSw128);
+        if (elect_one()) mma_bf16_ts(tm + warp * 16, tm + 256 + (kk % 20) * 8, bd, idesc, first ? 0u : 1u);
+        first = 0;
+      }
+      if (elect_one()) tc_commit(&bar);
+      __syncwarp();
+      mbar_wait(&bar, r & 1);
+      tot += clock64() - t0;
+    }
+    if (threadIdx.x == 0) out[0] = tot / reps;
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tm, 512); }
+}
+
+template <int NW>
+void runmw(long long *d) {
+  cudaFuncSetAttribute(kmw<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 70000);
+  for (int nm : {20, 24}) {
+    kmw<NW><<<1, 128, 70000>>>(d, nm, 50);
+    long long h = 0;
+    cudaError_t e = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+    printf("TS N=16, %d issuing warps, nmma=%2d: cycles=%lld  %s\n", NW, nm, h, cudaGetErrorString(e));
+  }
+}
+
 template <int N, bool TS, int NACC>
 void run(const char *name, long long *d) {
   cudaFuncSetAttribute(k<N, TS, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 70000);
@@ -59,6 +109,9 @@ void run(const char *name, long long *d) {
 int main() {
   long long *d;
   cudaMalloc(&d, 64);
+  runmw<1>(d);
+  runmw<2>(d);
+  runmw<4>(d);
   run<16, false, 1>("SS 1acc", d);
   run<16, true, 1>("TS 1acc", d);
   run<16, true, 4>("TS 4acc", d);
