@@ -35,6 +35,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -63,6 +64,7 @@ struct UttMeta {
   long long e_off;   // float offset of E_b
   long long ab_off;  // float offset of alpha_b / beta_b (2*pitch per frame)
   long long off_off; // float offset of this utterance's offset tables
+  long long vrow0;   // valid rows (frames of feasible utterances) before this utterance
 };
 
 struct CtcDev {
@@ -86,6 +88,7 @@ struct CtcDev {
   float *costs;           // [B]
   int *flags;             // [0]: non-finite cost seen
   int *argmax;            // optional [Tmax*B]: arg-max symbol per row (-1 on padded rows)
+  int dbg;                // tuning aid (B200CTC_DBG): ablation bits, wrong results
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -193,24 +196,24 @@ ctc_rowstats_gather_kernel(CtcDev d) {
       for (int u = 0; u < 8; u++) {
         float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
         if (mx > m) {
-          s *= exp2f((m - mx) * kLog2e);
+          s *= ex2_approx((m - mx) * kLog2e);
           m = mx;
           const int k0 = 4 * (k + 32 * u);
           am = v[u].x == mx ? k0 : (v[u].y == mx ? k0 + 1 : (v[u].z == mx ? k0 + 2 : k0 + 3));
         }
-        s += exp2f((v[u].x - m) * kLog2e) + exp2f((v[u].y - m) * kLog2e) +
-             exp2f((v[u].z - m) * kLog2e) + exp2f((v[u].w - m) * kLog2e);
+        s += ex2_approx((v[u].x - m) * kLog2e) + ex2_approx((v[u].y - m) * kLog2e) +
+             ex2_approx((v[u].z - m) * kLog2e) + ex2_approx((v[u].w - m) * kLog2e);
       }
     }
   } else {
     for (int k = lane; k < A; k += 32) {
       float v = __ldg(a + k);
       if (v > m) {
-        s *= exp2f((m - v) * kLog2e);
+        s *= ex2_approx((m - v) * kLog2e);
         m = v;
         am = k;
       }
-      s += exp2f((v - m) * kLog2e);
+      s += ex2_approx((v - m) * kLog2e);
     }
   }
   const float M = warp_max(m);
@@ -221,7 +224,7 @@ ctc_rowstats_gather_kernel(CtcDev d) {
     if (lane == 0) d.argmax[row] = cand;
     if (!um.feasible) return;
   }
-  s *= exp2f((m - M) * kLog2e);
+  s *= ex2_approx((m - M) * kLog2e);
   const float S = warp_sum(s);
   const float l2 = M * kLog2e + log2f(S);
   if (lane == 0) d.lse2[row] = l2;
@@ -317,6 +320,7 @@ __device__ __forceinline__ void ctc_ab_run(const CtcDev &d, const UttMeta &um, i
   float *off_out = (ROLE ? d.offB : d.offA) + um.off_off + r;
   const int o_step = ROLE ? -pitch2 : pitch2, e_step = ROLE ? -pitch : pitch;
   const bool writes_off = r < nthreads_needed;
+  const int off_stride = (nthreads_needed + 3) & ~3;
   float2 *bn_w = bnd + w;          // this warp's slot; the double buffer toggles by +-32
   int par = 0, rn = kRenorm, st = 0;
   uint32_t ph = 0;
@@ -357,7 +361,7 @@ __device__ __forceinline__ void ctc_ab_run(const CtcDev &d, const UttMeta &um, i
       if (block_end) {
         rn = kRenorm;
         if (writes_off) *off_out = c;
-        off_out += nthreads_needed;
+        off_out += off_stride;
         float mx = kNeg;
 #pragma unroll
         for (int p = 0; p < P; p++) mx = fmaxf(mx, fmaxf(hasX[p] ? X[p] : kNeg, hasY[p] ? Y[p] : kNeg));
@@ -493,7 +497,8 @@ __global__ void __launch_bounds__(kK3Warps * 32) ctc_grad_kernel(CtcDev d, int s
   const float *be = d.beta + um.ab_off + (long long)t * 2 * pitch + 1;
   const float *e = d.E + um.e_off + (long long)t * pitch;
   // offsets: alpha pair i = s/2 lives in thread i/P; beta pair i' = L - ceil(s/2)
-  const int P = d.P, nthr = (L + P) / P;
+  const int psh = d.P == 1 ? 0 : (d.P == 2 ? 1 : 2);             // P is 1, 2 or 4: shifts, not divisions
+  const int nthr = (((L + d.P) >> psh) + 3) & ~3;                // row stride of the offset tables
   const float *oa = d.offA + um.off_off + (long long)(t / kRenorm) * nthr;
   const float *ob = d.offB + um.off_off + (long long)((um.T - 1 - t) / kRenorm) * nthr;
   const double lp2 = d.logp2[b];
@@ -509,13 +514,13 @@ __global__ void __launch_bounds__(kK3Warps * 32) ctc_grad_kernel(CtcDev d, int s
       av[u] = ok ? al[s] : kNeg;
       bv[u] = ok ? be[s] : 0.f;
       ev[u] = ok ? ((s & 1) ? e[1 + (s >> 1)] : e[0]) : 0.f;
-      cv[u] = ok ? oa[(s >> 1) / P] + ob[(L - ((s + 1) >> 1)) / P] : 0.f;  // exact: integers
+      cv[u] = ok ? oa[(s >> 1) >> psh] + ob[(L - ((s + 1) >> 1)) >> psh] : 0.f;  // exact: integers
     }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int s = s0 + 32 * u;
       const float D = (float)((double)cv[u] - lp2);
-      const float v = exp2f(fminf(fmaxf((av[u] + bv[u] - ev[u]) + D, -200.f), 100.f));
+      const float v = ex2_approx(fminf(fmaxf((av[u] + bv[u] - ev[u]) + D, -200.f), 100.f));
       if (s < S) {
         z += v;
         if (s & 1) sm[s >> 1] = v;
@@ -541,22 +546,22 @@ __global__ void __launch_bounds__(kK3Warps * 32) ctc_grad_kernel(CtcDev d, int s
       for (int u = 0; u < 8; u++)
         if (k + 32 * u < n4) {
           float4 y;
-          y.x = gs * exp2f(v[u].x * kLog2e - l2);
-          y.y = gs * exp2f(v[u].y * kLog2e - l2);
-          y.z = gs * exp2f(v[u].z * kLog2e - l2);
-          y.w = gs * exp2f(v[u].w * kLog2e - l2);
+          y.x = gs * ex2_approx(v[u].x * kLog2e - l2);
+          y.y = gs * ex2_approx(v[u].y * kLog2e - l2);
+          y.z = gs * ex2_approx(v[u].z * kLog2e - l2);
+          y.w = gs * ex2_approx(v[u].w * kLog2e - l2);
           g4[k + 32 * u] = y;
         }
     }
   } else {
-    for (int k = lane; k < A; k += 32) g[k] = gs * exp2f(__ldg(a + k) * kLog2e - l2);
+    for (int k = lane; k < A; k += 32) g[k] = gs * ex2_approx(__ldg(a + k) * kLog2e - l2);
   }
   __syncwarp();  // orders the row stores above (and sm[]) before the per-label overwrites below
   const int *ul = d.uniq_lab + um.csr_off;
   const int *us = d.uniq_start + um.csr_off + b;  // nuniq+1 entries per utterance
   const int *pos = d.pos + um.lab_off;
 
-  if (lane == 0) g[d.blank] = gs * (exp2f(__ldg(a + d.blank) * kLog2e - l2) - zb * invZ);
+  if (lane == 0) g[d.blank] = gs * (ex2_approx(__ldg(a + d.blank) * kLog2e - l2) - zb * invZ);
   // overwrite the entries of the labels that occur.  Per-label posterior mass from shared memory in a
   // fixed order (deterministic); the activation gathers are L2 hits, four independent ones in flight.
   for (int j0 = lane; j0 < um.nuniq; j0 += 128) {
@@ -577,7 +582,267 @@ __global__ void __launch_bounds__(kK3Warps * 32) ctc_grad_kernel(CtcDev d, int s
     for (int i = 0; i < 4; i++) vv[i] = __ldg(a + kk[i]);
 #pragma unroll
     for (int i = 0; i < 4; i++)
-      if (j0 + 32 * i < um.nuniq) g[kk[i]] = gs * (exp2f(vv[i] * kLog2e - l2) - mass[i] * invZ);
+      if (j0 + 32 * i < um.nuniq) g[kk[i]] = gs * (ex2_approx(vv[i] * kLog2e - l2) - mass[i] * invZ);
+  }
+}
+
+// ===========================================================================
+// K3 (ring variant): gradient rows for wide alphabets, persistent, TMA-fed
+// ===========================================================================
+// The row-per-warp kernel above keeps only what its registers hold in flight, and every row starts with
+// a serial chain of table loads (alpha, beta, E, offsets) during which nothing streams: at A = 4000 it
+// reaches ~60 % of the copy bandwidth.  Here ONE persistent CTA per SM walks a contiguous range of valid
+// rows.  Thread 0 keeps two rings of TMA bulk copies ahead of the CTA: the activation rows (NA slots) and
+// the rows of the per-utterance tables (NT slots), so the memory system always has several rows per SM
+// outstanding while all 8 warps work on the current one out of shared memory:
+//   gamma (tables slot) | y = grad_scale*softmax in place (activation slot)      -- sync --
+//   label masses through the CSR (kept in shared memory per utterance), subtracted in place  -- sync --
+//   one TMA bulk store of the finished row (16 KB, full lines, no registers).
+// Padded rows and rows of infeasible utterances are zero-filled at the end.
+struct RingCfg {
+  int NA, NT;            // ring depths
+  int act_bytes;         // bytes per activation slot (A*4 rounded up to 128)
+  int tab_bytes;         // bytes per table slot
+  int pitch_max;
+  int pshift;            // log2(P)
+  long long vrow_base;   // meta[b_lo].vrow0
+  long long vrows;       // valid rows of this group
+};
+struct RowCur {
+  int b, t, T, L, pitch, nstr;
+  long long e_off, ab_off, off_off;
+};
+__device__ __forceinline__ void cur_load(const CtcDev &d, RowCur &c, int b, int pshift) {
+  const UttMeta um = d.meta[b];
+  c.b = b;
+  c.T = um.T;
+  c.L = um.L;
+  c.pitch = um.pitch;
+  c.nstr = ((((um.L + (1 << pshift)) >> pshift)) + 3) & ~3;
+  c.e_off = um.e_off;
+  c.ab_off = um.ab_off;
+  c.off_off = um.off_off;
+}
+__device__ __forceinline__ void cur_next(const CtcDev &d, RowCur &c, int b_end, int pshift) {
+  if (++c.t < c.T) return;
+  int b = c.b + 1;
+  while (b < b_end && !d.meta[b].feasible) b++;
+  c.t = 0;
+  if (b < b_end) cur_load(d, c, b, pshift);
+  else c.b = b_end;
+}
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
+               "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kRingConsumers = 256;                  // 8 consumer warps
+constexpr int kRingThreads = kRingConsumers + 32;    // + the producer warp
+
+__global__ void __launch_bounds__(kRingThreads, 2) ctc_grad_ring_kernel(CtcDev d, RingCfg rc) {
+  extern __shared__ __align__(128) unsigned char rsm[];
+  // barriers: full_act[NA] full_tab[NT] (TMA bytes) | done_act[NA] free_tab[NT] (one arrive per consumer warp)
+  uint64_t *full_act = reinterpret_cast<uint64_t *>(rsm);
+  uint64_t *full_tab = full_act + rc.NA;
+  uint64_t *done_act = full_tab + rc.NT;
+  uint64_t *free_tab = done_act + rc.NA;                           // 2*(NA+NT) <= 32 barriers = 256 B
+  float *partials = reinterpret_cast<float *>(rsm + 256);          // [2 rows][2][8]
+  unsigned char *act_base = rsm + 512;
+  unsigned char *tab_base = act_base + (size_t)rc.NA * rc.act_bytes;
+  float *gam0 = reinterpret_cast<float *>(tab_base + (size_t)rc.NT * rc.tab_bytes);  // [2 rows][pitch_max]
+  int *s_us = reinterpret_cast<int *>(gam0 + 2 * rc.pitch_max);    // [pitch_max + 4]
+  int *s_pos = s_us + rc.pitch_max + 4;                            // [pitch_max]
+  int *s_ul = s_pos + rc.pitch_max;                                // [pitch_max]
+
+  const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
+  const int A = d.A, b_end = d.b_lo + d.nb, pshift = rc.pshift;
+  const long long v_lo = rc.vrows * blockIdx.x / gridDim.x, v_hi = rc.vrows * (blockIdx.x + 1) / gridDim.x;
+  const int nrows = (int)(v_hi - v_lo);
+  const float gs = d.grad_scale;
+
+  if (tid == 0) {
+    for (int i = 0; i < rc.NA + rc.NT; i++) mbar_init(full_act + i, 1);
+    for (int i = 0; i < rc.NA + rc.NT; i++) mbar_init(done_act + i, kRingConsumers / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // first row of this CTA: the utterance that holds valid row v_lo
+  RowCur cur;
+  cur.b = b_end;
+  if (nrows > 0) {
+    int b = d.b_lo;
+    for (; b < b_end; b++) {
+      const UttMeta um = d.meta[b];
+      if (um.feasible && v_lo < um.vrow0 - rc.vrow_base + um.T) break;
+    }
+    cur_load(d, cur, b, pshift);
+    cur.t = (int)(v_lo - (d.meta[b].vrow0 - rc.vrow_base));
+  }
+
+  if (wi == kRingConsumers / 32) {
+    // ===================== producer: one thread keeps both rings full and drains finished rows =====
+    if (lane == 0 && nrows > 0) {
+      RowCur pa = cur, pt = cur, ps = cur;  // next activation row / next table row to request / next row to store
+      auto issue_act = [&](int i) {
+        uint64_t *bar = full_act + (i % rc.NA);
+        mbar_expect_tx(bar, (uint32_t)A * 4u);
+        tma_load_1d(act_base + (size_t)(i % rc.NA) * rc.act_bytes, d.act + ((long long)pa.t * d.B + pa.b) * A,
+                    (uint32_t)A * 4u, bar);
+        cur_next(d, pa, b_end, pshift);
+      };
+      auto issue_tab = [&](int i) {
+        uint64_t *bar = full_tab + (i % rc.NT);
+        float *dst = reinterpret_cast<float *>(tab_base + (size_t)(i % rc.NT) * rc.tab_bytes);
+        const int p = pt.pitch, ns = pt.nstr;
+        mbar_expect_tx(bar, (uint32_t)(5 * p + 2 * ns) * 4u);
+        tma_load_1d(dst, d.alpha + pt.ab_off + (long long)pt.t * 2 * p, (uint32_t)p * 8u, bar);
+        tma_load_1d(dst + 2 * p, d.beta + pt.ab_off + (long long)pt.t * 2 * p, (uint32_t)p * 8u, bar);
+        tma_load_1d(dst + 4 * p, d.E + pt.e_off + (long long)pt.t * p, (uint32_t)p * 4u, bar);
+        tma_load_1d(dst + 5 * p, d.offA + pt.off_off + (long long)(pt.t / kRenorm) * ns, (uint32_t)ns * 4u, bar);
+        tma_load_1d(dst + 5 * p + ns, d.offB + pt.off_off + (long long)((pt.T - 1 - pt.t) / kRenorm) * ns,
+                    (uint32_t)ns * 4u, bar);
+        cur_next(d, pt, b_end, pshift);
+      };
+      for (int i = 0; i < min(rc.NT, nrows); i++) issue_tab(i);
+      for (int i = 0; i < min(rc.NA - 1, nrows); i++) issue_act(i);
+      for (int i = 0; i < nrows; i++) {
+        if (i + rc.NT < nrows) {  // the consumers are done with row i's tables -> that slot takes row i+NT
+          mbar_wait(free_tab + (i % rc.NT), (uint32_t)(i / rc.NT) & 1u);
+          issue_tab(i + rc.NT);
+        }
+        mbar_wait(done_act + (i % rc.NA), (uint32_t)(i / rc.NA) & 1u);  // row i finished in its slot
+        bulk_store(d.grad + ((long long)ps.t * d.B + ps.b) * A, act_base + (size_t)(i % rc.NA) * rc.act_bytes,
+                   (uint32_t)A * 4u);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        cur_next(d, ps, b_end, pshift);
+        // the slot of row i-1 (its store was committed one row ago) takes row i+NA-1
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (i + rc.NA - 1 < nrows) issue_act(i + rc.NA - 1);
+      }
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  } else {
+    // ===================== consumers: 8 warps on one row at a time ================================
+    int loaded_b = -1, nuniq = 0;
+    float lp_hi = 0.f, lp_lo = 0.f;
+    for (int i = 0; i < nrows; i++) {
+      if (cur.b != loaded_b) {  // new utterance: its label -> positions CSR into shared memory
+        named_bar_sync(1, kRingConsumers);
+        const UttMeta um = d.meta[cur.b];
+        nuniq = um.nuniq;
+        const int *ul = d.uniq_lab + um.csr_off, *us = d.uniq_start + um.csr_off + cur.b, *pos = d.pos + um.lab_off;
+        for (int k = tid; k <= nuniq; k += kRingConsumers) s_us[k] = us[k];
+        for (int k = tid; k < nuniq; k += kRingConsumers) s_ul[k] = ul[k];
+        for (int k = tid; k < um.L; k += kRingConsumers) s_pos[k] = pos[k];
+        // log2 p(l|x) split into an integer and a fraction: (offset sum - integer) is exact in fp32
+        const double lp2 = d.logp2[cur.b];
+        const double fl = floor(lp2);
+        lp_hi = (float)fl;
+        lp_lo = (float)(lp2 - fl);
+        loaded_b = cur.b;
+        named_bar_sync(1, kRingConsumers);
+      }
+      const long long row = (long long)cur.t * d.B + cur.b;
+      const float l2 = __ldg(d.lse2 + row);  // needed only after the gamma phase
+      const int L = cur.L, S = 2 * L + 1, p = cur.pitch, ns = cur.nstr;
+      float *gam = gam0 + (i & 1) * rc.pitch_max;
+      float *part = partials + (i & 1) * 16;
+
+      // ---- gamma_t(s) ~ 2^(alpha + beta - E + offsets - log2 p), label states to gam[], sums for Z
+      const float *tab = reinterpret_cast<const float *>(tab_base + (size_t)(i % rc.NT) * rc.tab_bytes);
+      const float *al = tab, *be = tab + 2 * p + 1, *e = tab + 4 * p, *oa = tab + 5 * p, *ob = oa + ns;
+      mbar_wait(full_tab + (i % rc.NT), (uint32_t)(i / rc.NT) & 1u);
+      float z = 0.f, zblank = 0.f;
+      const float eb = e[0];
+      if (!(d.dbg & 2)) {
+        // one (blank, label) pair per thread and iteration: states 2i and 2i+1
+        for (int i2 = tid; i2 <= L; i2 += kRingConsumers) {
+          const float2 a2 = *reinterpret_cast<const float2 *>(al + 2 * i2);
+          const float b0 = be[2 * i2], b1 = be[2 * i2 + 1];
+          const float o_a = oa[i2 >> pshift];
+          const float c0 = o_a + ob[(L - i2) >> pshift];          // state 2i   (exact: integers)
+          const float v0 = ex2_approx(fminf(fmaxf((a2.x + b0 - eb) + ((c0 - lp_hi) - lp_lo), -200.f), 100.f));
+          z += v0;
+          zblank += v0;
+          if (i2 < L) {
+            const float c1 = o_a + ob[(L - i2 - 1) >> pshift];    // state 2i+1
+            const float v1 =
+                ex2_approx(fminf(fmaxf((a2.y + b1 - e[1 + i2]) + ((c1 - lp_hi) - lp_lo), -200.f), 100.f));
+            z += v1;
+            gam[i2] = v1;
+          }
+        }
+      }
+      z = warp_sum(z);
+      zblank = warp_sum(zblank);
+      if (lane == 0) {
+        part[wi] = z;
+        part[8 + wi] = zblank;
+        mbar_arrive(free_tab + (i % rc.NT));  // (shuffles above: every lane of the warp is past its table reads)
+      }
+
+      // ---- y = grad_scale * softmax(row), in place in the activation slot
+      float4 *a4 = reinterpret_cast<float4 *>(act_base + (size_t)(i % rc.NA) * rc.act_bytes);
+      mbar_wait(full_act + (i % rc.NA), (uint32_t)(i / rc.NA) & 1u);
+      const int n4 = (d.dbg & 16) ? 0 : (A >> 2);
+      for (int k0 = tid; k0 < n4; k0 += 4 * kRingConsumers) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (k0 + u * kRingConsumers < n4) v[u] = a4[k0 + u * kRingConsumers];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (k0 + u * kRingConsumers < n4) {
+            v[u].x = gs * ex2_approx(v[u].x * kLog2e - l2);
+            v[u].y = gs * ex2_approx(v[u].y * kLog2e - l2);
+            v[u].z = gs * ex2_approx(v[u].z * kLog2e - l2);
+            v[u].w = gs * ex2_approx(v[u].w * kLog2e - l2);
+            a4[k0 + u * kRingConsumers] = v[u];
+          }
+      }
+      named_bar_sync(1, kRingConsumers);  // gam[], part[] and the scaled row are complete
+
+      // ---- subtract the posterior mass of every distinct label (fixed summation order) and of the blank
+      float Z = 0.f, zb = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        Z += part[k];
+        zb += part[8 + k];
+      }
+      const float invZ = Z > 0.f ? 1.0f / Z : 0.f;
+      float *arow = reinterpret_cast<float *>(a4);
+      if (!(d.dbg & 1)) {
+        for (int j = tid; j < nuniq; j += kRingConsumers) {
+          const int q0 = s_us[j], q1 = s_us[j + 1];
+          float acc = gam[s_pos[q0]];
+          for (int q = q0 + 1; q < q1; q++) acc += gam[s_pos[q]];
+          arow[s_ul[j]] -= gs * (acc * invZ);
+        }
+      }
+      if (tid == 0) arow[d.blank] -= gs * (zb * invZ);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk store
+      __syncwarp();
+      if (lane == 0) mbar_arrive(done_act + (i % rc.NA));
+      cur_next(d, cur, b_end, pshift);
+    }
+  }
+
+  // ---- zero rows: padded frames and infeasible utterances of this group
+  if (wi < kRingConsumers / 32) {
+    const long long rows = (long long)d.Tmax * d.nb;
+    for (long long lrow = (long long)blockIdx.x * 8 + wi; lrow < rows; lrow += (long long)gridDim.x * 8) {
+      const int t = (int)(lrow / d.nb), b = d.b_lo + (int)(lrow - (long long)t * d.nb);
+      const int Tb = d.meta[b].T, feas = d.meta[b].feasible;
+      if (t < Tb && feas) continue;
+      float4 *g4 = reinterpret_cast<float4 *>(d.grad + ((long long)t * d.B + b) * A);
+      for (int k = lane; k < (A >> 2); k += 32) g4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 }
 
@@ -617,7 +882,7 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int A,
     m.e_off = e_off;
     m.ab_off = ab_off;
     m.off_off = off_off;
-    off_off += (long long)((T + kRenorm - 1) / kRenorm) * (L + 1);
+    off_off += (long long)((T + kRenorm - 1) / kRenorm) * m.pitch;  // row stride <= align4(L+1) for any P
     e_off += (long long)T * m.pitch;
     ab_off += (long long)T * 2 * m.pitch;
     p->sumT += T;
@@ -697,6 +962,7 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
     return CTC_STATUS_INVALID_VALUE;
   if (opt.blank_label < 0 || opt.blank_label >= A) return CTC_STATUS_INVALID_VALUE;
   if ((uintptr_t)workspace % 256 != 0) return CTC_STATUS_INVALID_VALUE;
+  const auto host_t0 = std::chrono::steady_clock::now();
   Plan p;
   ctcStatus_t st = make_plan(label_lengths, input_lengths, A, B, &p);
   if (st != CTC_STATUS_SUCCESS) return st;
@@ -719,6 +985,7 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
     slot.assign(A, 0);
   }
   static thread_local int epoch = 0;
+  long long vrows_total = 0;
   for (int b = 0; b < B; b++) {
     UttMeta &m = p.meta[b];
     const int *lab = flat_labels + m.lab_off;
@@ -752,6 +1019,8 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
     us[nu] = m.L;
     for (int i = 0; i < m.L; i++) hpos[m.lab_off + cnt[slot[lab[i]]]++] = i;
     m.nuniq = nu;
+    m.vrow0 = vrows_total;
+    if (m.feasible) vrows_total += m.T;
     hm[b] = m;
   }
   unsigned char *w = static_cast<unsigned char *>(workspace);
@@ -783,6 +1052,8 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   dev.costs = reinterpret_cast<float *>(w + p.off_costs);
   dev.flags = reinterpret_cast<int *>(w + p.off_flags);
   dev.argmax = opt.argmax_dev;
+  static const int dbg = getenv("B200CTC_DBG") ? atoi(getenv("B200CTC_DBG")) : 0;
+  dev.dbg = dbg;
 
   // K2 geometry: P pairs per thread so that one direction fits 512 threads
   const int npairs = p.maxL + 1;
@@ -806,59 +1077,128 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
       smem3_set = smem3;
     }
   }
+  // Wide alphabets: the persistent TMA-ring gradient kernel (see ctc_grad_ring_kernel)
+  static int num_sms = 0;
+  if (!num_sms) {
+    int devid = 0;
+    cudaGetDevice(&devid);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, devid);
+  }
+  const int env_ring = getenv("B200CTC_RING") ? atoi(getenv("B200CTC_RING")) : -1;   // tuning aids
+  static const int env_na = getenv("B200CTC_NA") ? atoi(getenv("B200CTC_NA")) : 0;
+  static const int env_nt = getenv("B200CTC_NT") ? atoi(getenv("B200CTC_NT")) : 0;
+  RingCfg rc;
+  rc.NA = env_na >= 2 ? env_na : 4;
+  rc.NT = env_nt >= 1 ? env_nt : 2;
+  rc.act_bytes = (int)align_up((size_t)A * 4, 128);
+  rc.tab_bytes = (int)align_up((size_t)7 * p.pitch_max * 4, 128);
+  rc.pitch_max = p.pitch_max;
+  rc.pshift = P == 1 ? 0 : (P == 2 ? 1 : 2);
+  rc.vrow_base = rc.vrows = 0;
+  auto ring_bytes = [&]() {
+    return (size_t)512 + (size_t)rc.NA * rc.act_bytes + (size_t)rc.NT * rc.tab_bytes +
+           sizeof(float) * ((size_t)5 * p.pitch_max + 8);
+  };
+  // two CTAs per SM (16 consumer warps keep the issue slots busy): <= ~113 KB each
+  bool use_ring = grad && (A & 3) == 0 && A >= 1024 && (size_t)p.Tmax * B * A >= ((size_t)64 << 20);
+  if (env_ring == 1 && grad && (A & 3) == 0) use_ring = true;
+  if (env_ring == 0) use_ring = false;
+  while (use_ring && ring_bytes() > ((size_t)113 << 10) && rc.NA > 3) rc.NA--;
+  if (ring_bytes() > ((size_t)113 << 10) || rc.NA + rc.NT > 16) use_ring = false;
+  const size_t ring_smem = ring_bytes();
+  if (use_ring) {
+    static size_t ring_set = 0;
+    if (ring_smem > ring_set) {
+      if (cudaFuncSetAttribute(ctc_grad_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)ring_smem) != cudaSuccess)
+        return CTC_STATUS_EXECUTION_FAILED;
+      ring_set = ring_smem;
+    }
+  }
   // tuning aid: B200CTC_PROFILE=1 serialises the groups and prints the duration of each kernel
-  const bool prof = getenv("B200CTC_PROFILE") != nullptr;
+  static const int prof_mode = getenv("B200CTC_PROFILE") ? atoi(getenv("B200CTC_PROFILE")) : 0;
+  const bool prof = prof_mode == 1;
+  const bool timeline = prof_mode == 2;   // keeps the groups; prints each kernel's start/end on its own stream
   // (only worth it when the row kernels are long: a slab of >= 256 MB)
   const bool big = (size_t)p.Tmax * B * A >= ((size_t)64 << 20);
   // Utterance groups on separate streams: the latency-bound alpha/beta recursion of one group runs
   // under the bandwidth-bound row kernels of the others (only the first K2 and the last K3 stay exposed).
   constexpr int kMaxGroups = 8;
-  static const int env_groups = getenv("B200CTC_GROUPS") ? atoi(getenv("B200CTC_GROUPS")) : 0;
+  const int env_groups = getenv("B200CTC_GROUPS") ? atoi(getenv("B200CTC_GROUPS")) : 0;
   int ngroups = B >= 16 ? 2 : 1;   // measured at B=256, A=4000: 1 -> 10.47 ms, 2 -> 9.95, 4 -> 9.91, 8 -> 9.99
+  if (!big) ngroups = 1;
   if (env_groups >= 1 && env_groups <= kMaxGroups) ngroups = std::min(env_groups, B);
-  if (!big || prof || getenv("B200CTC_ONE_STREAM")) ngroups = 1;
-  static cudaStream_t side[kMaxGroups] = {};
-  static cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {};
-  if (ngroups > 1 && !ev_fork &&
-      cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess)
-    return CTC_STATUS_EXECUTION_FAILED;
-  for (int gi = 1; gi < ngroups; gi++) {
-    if (!side[gi] && (cudaStreamCreateWithFlags(&side[gi], cudaStreamNonBlocking) != cudaSuccess ||
-                      cudaEventCreateWithFlags(&ev_join[gi], cudaEventDisableTiming) != cudaSuccess))
-      return CTC_STATUS_EXECUTION_FAILED;
-  }
+  if (prof || getenv("B200CTC_ONE_STREAM")) ngroups = 1;
+  // Several groups: the row kernels (K1, K3) of all groups run back to back on the caller's stream; each
+  // group's alpha/beta kernel runs on its own HIGH-PRIORITY stream between them, so its CTAs are placed as
+  // soon as the group's K1 is done instead of queueing behind the row kernels of the other groups.
+  static cudaStream_t hp[kMaxGroups] = {};
+  static cudaEvent_t e1[kMaxGroups] = {}, e2[kMaxGroups] = {};
   if (ngroups > 1) {
-    cudaEventRecord(ev_fork, stream);  // header copy + prior work of the caller's stream
-    for (int gi = 1; gi < ngroups; gi++) cudaStreamWaitEvent(side[gi], ev_fork, 0);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    for (int gi = 0; gi < ngroups; gi++)
+      if (!hp[gi] && (cudaStreamCreateWithPriority(&hp[gi], cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+                      cudaEventCreateWithFlags(&e1[gi], cudaEventDisableTiming) != cudaSuccess ||
+                      cudaEventCreateWithFlags(&e2[gi], cudaEventDisableTiming) != cudaSuccess))
+        return CTC_STATUS_EXECUTION_FAILED;
+  }
+  cudaEvent_t tl[kMaxGroups][4], tl0;
+  if (timeline) {
+    fprintf(stderr, "[b200ctc] host preparation %.3f ms\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
+    cudaEventCreate(&tl0);
+    for (int gi = 0; gi < ngroups; gi++)
+      for (int i = 0; i < 4; i++) cudaEventCreate(&tl[gi][i]);
+    cudaEventRecord(tl0, stream);
   }
   cudaEvent_t ev[4];
   if (prof) {
     for (int i = 0; i < 4; i++) cudaEventCreate(&ev[i]);
     cudaEventRecord(ev[0], stream);
   }
-  for (int gi = 0; gi < ngroups; gi++) {
-    cudaStream_t st = gi == 0 ? stream : side[gi];
+  auto set_group = [&](int gi) {
     dev.b_lo = (int)((long long)B * gi / ngroups);
     dev.nb = (int)((long long)B * (gi + 1) / ngroups) - dev.b_lo;
-    const long long rows = (long long)p.Tmax * dev.nb;
+    return (long long)p.Tmax * dev.nb;
+  };
+  for (int gi = 0; gi < ngroups; gi++) {  // K1
+    const long long rows = set_group(gi);
     const unsigned g1 = (unsigned)((rows + kK1Warps - 1) / kK1Warps);
-    ctc_rowstats_gather_kernel<<<g1, kK1Warps * 32, 0, st>>>(dev);
+    if (timeline) cudaEventRecord(tl[gi][0], stream);
+    ctc_rowstats_gather_kernel<<<g1, kK1Warps * 32, 0, stream>>>(dev);
     if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
-    if (prof) cudaEventRecord(ev[1], st);
+    if (timeline) cudaEventRecord(tl[gi][1], stream);
+    if (ngroups > 1) cudaEventRecord(e1[gi], stream);
+  }
+  if (prof) cudaEventRecord(ev[1], stream);
+  for (int gi = 0; gi < ngroups; gi++) {  // K2
+    set_group(gi);
+    cudaStream_t st = ngroups > 1 ? hp[gi] : stream;
+    if (ngroups > 1) cudaStreamWaitEvent(st, e1[gi], 0);
     cudaError_t ce = P == 1   ? launch_k2<1>(dev, B, NT, F, st)
                      : P == 2 ? launch_k2<2>(dev, B, NT, F, st)
                               : launch_k2<4>(dev, B, NT, F, st);
     if (ce != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
-    if (prof) cudaEventRecord(ev[2], st);
-    if (grad) {
+    if (timeline) cudaEventRecord(tl[gi][2], st);
+    if (ngroups > 1) cudaEventRecord(e2[gi], st);
+  }
+  if (prof) cudaEventRecord(ev[2], stream);
+  for (int gi = 0; gi < ngroups; gi++) {  // K3
+    const long long rows = set_group(gi);
+    if (ngroups > 1) cudaStreamWaitEvent(stream, e2[gi], 0);  // (also joins the side stream back)
+    if (grad && use_ring) {
+      rc.vrow_base = p.meta[dev.b_lo].vrow0;
+      rc.vrows = (dev.b_lo + dev.nb < B ? p.meta[dev.b_lo + dev.nb].vrow0 : vrows_total) - rc.vrow_base;
+      const unsigned g3 = (unsigned)std::max<long long>(1, std::min<long long>(2 * num_sms, (rows + 7) / 8));
+      ctc_grad_ring_kernel<<<g3, kRingThreads, ring_smem, stream>>>(dev, rc);
+      if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
+    } else if (grad) {
       const unsigned g3 = (unsigned)((rows + kK3Warps - 1) / kK3Warps);
-      ctc_grad_kernel<<<g3, kK3Warps * 32, smem3, st>>>(dev, smem_pitch);
+      ctc_grad_kernel<<<g3, kK3Warps * 32, smem3, stream>>>(dev, smem_pitch);
       if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
     }
-  }
-  for (int gi = 1; gi < ngroups; gi++) {
-    cudaEventRecord(ev_join[gi], side[gi]);
-    cudaStreamWaitEvent(stream, ev_join[gi], 0);
+    if (timeline) cudaEventRecord(tl[gi][3], stream);
   }
   if (prof) {
     cudaEventRecord(ev[3], stream);
@@ -870,6 +1210,18 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
     fprintf(stderr, "[b200ctc] B=%d A=%d Tmax=%d maxL=%d P=%d F=%d: rowstats %.3f ms, alpha_beta %.3f ms, grad %.3f ms\n",
             B, A, p.Tmax, p.maxL, P, F, t1, t2, t3);
     for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]);
+  }
+  if (timeline) {
+    cudaStreamSynchronize(stream);
+    for (int gi = 0; gi < ngroups; gi++) {
+      float t[4];
+      for (int i = 0; i < 4; i++) {
+        cudaEventElapsedTime(&t[i], tl0, tl[gi][i]);
+        cudaEventDestroy(tl[gi][i]);
+      }
+      fprintf(stderr, "[b200ctc] group %d/%d: K1 %.3f..%.3f  K2 ..%.3f  K3 ..%.3f ms\n", gi, ngroups, t[0], t[1], t[2], t[3]);
+    }
+    cudaEventDestroy(tl0);
   }
   if (costs_dev &&
       cudaMemcpyAsync(costs_dev, dev.costs, sizeof(float) * B, cudaMemcpyDeviceToDevice, stream) !=
