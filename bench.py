@@ -160,7 +160,7 @@ def ctc_roofline(dev, pk, pk_src, B=256):
     pitch = (L.astype(np.int64) + 1 + 3) // 4 * 4
     tables = float((T.astype(np.int64) * pitch * 5 * 2 * 4).sum())
     physical = 2.0 * 4 * A * float(T.sum()) + 4.0 * A * Tmax * B + tables
-    traffic, traffic_src = ncu_traffic("ctc_grad")
+    traffic, traffic_src = ncu_traffic("ctc_grad_ring")
     return {"workload": "configs[4]: A=4000, B=%d, T_b~U{1500..3000}, L_b~U{50..600}, 1 GPU" % B, "bound": "hbm",
             "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
             "ms_per_call": ms, "algorithmic_bytes": int(nbytes), "peak_source": pk_src,
