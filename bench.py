@@ -166,7 +166,7 @@ def ctc_roofline(dev, pk, pk_src, B=256):
             "ms_per_call": ms, "algorithmic_bytes": int(nbytes), "peak_source": pk_src,
             "physical_bytes_3_passes_plus_tables": int(physical), "physical_GBps": physical / ms / 1e6,
             "physical_frac": physical / ms / 1e6 / pk["hbm_gbs"],
-            "traffic": traffic, "traffic_source": (traffic_src + " (ctc_grad_kernel, B=32 slice)") if traffic_src else None,
+            "traffic": traffic, "traffic_source": (traffic_src + " (ctc_grad_ring_kernel, B=32 slice)") if traffic_src else None,
             "costs_finite": bool(np.isfinite(costs).all() and (costs > 0).all()),
             "l2": "inputs (12.3 GB) + outputs (12.3 GB) >> 126 MB L2"}
 

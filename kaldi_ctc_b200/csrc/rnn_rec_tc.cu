@@ -27,6 +27,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "rnn_common.cuh"
 #include "tc_common.cuh"
@@ -44,6 +45,11 @@ constexpr int kIssuers = 4;     // MMA-issuing warps: the burst of small MMAs is
                                 // emits around every tcgen05.mma (tools/mma_bench.cu: 20 MMAs in 1135 / 855 / 480 cycles
                                 // with 1 / 2 / 4 issuing warps), so four warps issue a quarter of the K slices each
 constexpr int kThreads = 32 * kIssuers + 128;   // warps 0-3: MMA issuers (one accumulator each), warps 4-7: epilogue
+// EH = 2 ("split epilogue", batch chunks of 8 / 16): warps 8-11 are a second set of epilogue warps.  A TMEM lane
+// quarter can only be read by warps with the same (warp % 4), so warps q and q+4 share a quarter and each takes
+// half of the chunk's utterance columns: the per-thread epilogue work -- which is on the per-step critical
+// chain -- halves.
+__host__ __device__ constexpr int threads_of(int EH) { return 32 * kIssuers + 128 * EH; }
 constexpr int kTmemCols = 256;  // D: columns [0,64) (four accumulators); A (R slice): columns [64, 64 + H/2)
 constexpr int kRingOffset = 48 * 1024;   // forward kernel: cp.async prefetch ring (32 KB) behind the h tiles + barriers
 constexpr int kACol = 64;       // (several independent accumulators were measured: no gain, the
@@ -112,10 +118,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // forward
 // ===========================================================================
 // smem: [Rs: nkb x 128 rows x 128 B][hs: 2 x nkb x 16 rows x 128 B][barriers]
-template <int MODE, int NJ, int NKB>
-__global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
+template <int MODE, int NJ, int NKB, int EH>
+__global__ void __launch_bounds__(threads_of(EH), 1) rec_tc_fwd_kernel(RecArgs a) {
   constexpr int G = MODE == 2 ? 4 : (MODE == 3 ? 3 : 1);
   constexpr int BC = 4 * NJ;
+  constexpr int NJL = NJ / EH, BCL = 4 * NJL;   // utterance groups / columns per epilogue thread
+  constexpr int kThreads = threads_of(EH);
+  static_assert(NJ % EH == 0, "split epilogue needs an even number of utterance groups");
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
   const int NC = a.NC;
@@ -157,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // ---- one-time: my 128 gate rows of R -> BF16 -> tensor memory (lane = row, column = k/2)
-  if (warp >= kIssuers) {
+  if (warp >= kIssuers && warp < kIssuers + 4) {
     const int q = warp & 3, row = q * 32 + lane;
     const int u = row >> 2, g = row & 3;
     const float *src = a.w_rec[dir] + ((size_t)(g < G ? g : 0) * H + crank * UT + u) * H;
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
         // tcgen05.commit arrive ~60 cycles after its last MMA, warps sleeping on the mbarrier were
         // measured to resume ~300 cycles later
         mbar_wait(acc_full, step & 1);
-        asm volatile("bar.arrive 2, 160;" ::: "memory");
+        asm volatile("bar.arrive 2, %0;" ::"n"(32 + 128 * EH) : "memory");
       }
       if (prof) {
         const long long m4 = clock64();
@@ -242,6 +251,8 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;                  // TMEM lane quarter
+    const int eh = (warp - kIssuers) >> 2;   // which half of the chunk's columns (split epilogue)
+    const int jb = eh * NJL;                 // my first utterance group
     const int s = lane & 3;                  // gate slot of my row / batch slot after the transpose
     const int ul = q * 8 + (lane >> 2);      // local unit 0..31
     const int unit = crank * UT + ul;
@@ -249,9 +260,9 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
     float *cell = a.cell[dir];
     float brn = 0.f;
     if (MODE == 3) brn = a.b_rec[dir][2 * H + unit];
-    float cst[NJ], hst[NJ];                  // cell / hidden state of (unit, batch 4j+s), fp32
+    float cst[NJL], hst[NJL];                // cell / hidden state of (unit, batch 4(jb+j)+s), fp32
 #pragma unroll
-    for (int j = 0; j < NJ; j++) cst[j] = hst[j] = 0.f;
+    for (int j = 0; j < NJL; j++) cst[j] = hst[j] = 0.f;
 
     // which pre-activation column this ROW needs: LSTM gate s; GRU slots 0,1 -> r,z,
     // slot 3 carries the input part of n (slot 2 = recurrent part, nothing to load)
@@ -262,23 +273,24 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
     // synchronisation).  Register prefetch one step ahead cost 12 % of the step at T = 2000 (HBM latency
     // tails of the slowest thread of the slowest CTA gate every step); 2 / 4 steps ahead recovered 11 / 15 %.
     constexpr int kPF = BC == 4 ? 16 : (BC == 8 ? 8 : 4);
-    float *pring = reinterpret_cast<float *>(smem + kRingOffset) + (size_t)(tid - 32 * kIssuers) * BC;   // + slot * 128 * BC
+    // [slot][quarter thread 0..127][BC columns]; a thread owns columns [eh * BCL, eh * BCL + BCL)
+    float *pring = reinterpret_cast<float *>(smem + kRingOffset) + (size_t)((tid - 32 * kIssuers) & 127) * BC + eh * BCL;
     auto issue_pre = [&](int step) {
       if (step < T && pload && !(a.dbg_flags & 2)) {
         const int t = dir ? T - 1 - step : step;
         const float *pp = gates + ((size_t)t * B + b_lo) * GH + (size_t)pcol * H + unit;
         const uint32_t dst = smem_u32(pring + (size_t)(step % kPF) * 128 * BC);
 #pragma unroll
-        for (int b = 0; b < BC; b++)
-          if (b < nb)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4 * b), "l"(pp + (size_t)b * GH) : "memory");
+        for (int b = 0; b < BCL; b++)
+          if (eh * BCL + b < nb)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4 * b), "l"(pp + (size_t)(eh * BCL + b) * GH) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
 #pragma unroll
     for (int k = 0; k < kPF; k++) {   // slots of (thread, b) pairs that are never copied stay zero
 #pragma unroll
-      for (int b = 0; b < BC; b++) pring[(size_t)k * 128 * BC + b] = 0.f;
+      for (int b = 0; b < BCL; b++) pring[(size_t)k * 128 * BC + b] = 0.f;
     }
     for (int k = 0; k < kPF; k++) issue_pre(k);
 
@@ -299,33 +311,34 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
       const long long c0 = prof ? clock64() : 0;
       // this step's projection rows (copied kPF steps ago)
       asm volatile("cp.async.wait_group %0;" ::"n"(kPF - 1) : "memory");
-      float pre[BC];
+      float pre[BCL];
       {
         const float *ps = pring + (size_t)(step % kPF) * 128 * BC;
 #pragma unroll
-        for (int b = 0; b < BC; b++) pre[b] = ps[b];
+        for (int b = 0; b < BCL; b++) pre[b] = ps[b];
       }
-      asm volatile("bar.sync 2, 160;" ::: "memory");
+      asm volatile("bar.sync 2, %0;" ::"n"(32 + 128 * EH) : "memory");
       const long long c1a = prof ? clock64() : 0;
       if (!(a.dbg_flags & 4)) tc_fence_after();
       const long long c1 = prof ? clock64() : 0;
       if (prof && lane == 0) a.dbg[16] += c1 - c1a;
       // only the BC columns of each issuer's accumulator that this chunk uses (TMEM reads are paced by bytes)
-      uint32_t ra[kIssuers][BC];
+      uint32_t ra[kIssuers][BCL];
 #pragma unroll
-      for (int w = 0; w < kIssuers; w++) tmem_ld_32xN<BC>(tmem_base + ((uint32_t)(q * 32) << 16) + w * NPAD, ra[w]);
+      for (int w = 0; w < kIssuers; w++)
+        tmem_ld_32xN<BCL>(tmem_base + ((uint32_t)(q * 32) << 16) + w * NPAD + eh * BCL, ra[w]);
       tmem_ld_wait();
       tc_fence_before();
-      float r[BC];  // the issuers' partial sums, added in a fixed order
+      float r[BCL];  // the issuers' partial sums, added in a fixed order
 #pragma unroll
-      for (int e = 0; e < BC; e++)
+      for (int e = 0; e < BCL; e++)
         r[e] = (__uint_as_float(ra[0][e]) + __uint_as_float(ra[1][e])) + (__uint_as_float(ra[2][e]) + __uint_as_float(ra[3][e]));
       const long long c2 = prof ? clock64() : 0;
 
       // ---- gates -> (unit, batch) threads, cell update; results kept in registers
-      float hnew[NJ], sv[NJ][4], sc[NJ];
+      float hnew[NJL], sv[NJL][4], sc[NJL];
 #pragma unroll
-      for (int j = 0; j < NJ; j++) {
+      for (int j = 0; j < NJL; j++) {
         float x[4], g[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
@@ -342,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
           }
         }
         quad_transpose(x, g, s);
-        const bool valid = 4 * j + s < nb;
+        const bool valid = 4 * (jb + j) + s < nb;
         float h;
         if (MODE == 2) {
           cst[j] = fmaf(g[1], cst[j], g[0] * g[2]);
@@ -370,8 +383,8 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
       if (step + 1 < T) {
         const int pn = (step + 1) & 1;
 #pragma unroll
-        for (int j = 0; j < NJ; j++) {
-          // pack 8 consecutive units (one warp) of batch 4j+s into one 16-byte chunk
+        for (int j = 0; j < NJL; j++) {
+          // pack 8 consecutive units (one warp) of batch 4(jb+j)+s into one 16-byte chunk
           const float v = hnew[j];
           const float pv = __shfl_xor_sync(0xffffffffu, v, 4);
           const uint32_t pair = (lane & 4) ? pack_bf16(pv, v) : pack_bf16(v, pv);
@@ -382,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
           uint4 ch;
           if (lane & 16) ch = make_uint4(lo2, hi2, lo, hi);
           else ch = make_uint4(lo, hi, lo2, hi2);
-          const int b = 4 * j + s;
+          const int b = 4 * (jb + j) + s;
           const uint32_t off = pn * hs_bytes + kb_mine * 2048 + b * 128 + ((chunk_mine ^ (b & 7)) << 4);
           if (peer_a < NC) st_async_v4(rhs_a + off, ch.x, ch.y, ch.z, ch.w, rhf_a + pn * 8);
           if (peer_b < NC) st_async_v4(rhs_b + off, ch.x, ch.y, ch.z, ch.w, rhf_b + pn * 8);
@@ -392,8 +405,8 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
 
       // ---- off the critical path: results to HBM, next step's projection prefetch
 #pragma unroll
-      for (int j = 0; j < NJ; j++) {
-        const int b = 4 * j + s;
+      for (int j = 0; j < NJL; j++) {
+        const int b = 4 * (jb + j) + s;
         if (b < nb && !(a.dbg_flags & 1)) {
           const size_t row = (size_t)t * B + b_lo + b;
           a.y[row * HO + dir * H + unit] = hnew[j];
@@ -440,10 +453,13 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_fwd_kernel(RecArgs a) {
 // (= the 32 units of exactly one peer CTA) into that peer's receive buffer: a
 // reduce-scatter over distributed shared memory, completion counted on the
 // peer's mbarrier.
-template <int MODE, int NJ>
-__global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
+template <int MODE, int NJ, int EH>
+__global__ void __launch_bounds__(threads_of(EH), 1) rec_tc_bwd_kernel(RecArgs a) {
   constexpr int G = MODE == 2 ? 4 : (MODE == 3 ? 3 : 1);
   constexpr int BC = 4 * NJ;
+  constexpr int NJL = NJ / EH, BCL = 4 * NJL;   // utterance groups / columns per epilogue thread
+  constexpr int kThreads = threads_of(EH);
+  static_assert(NJ % EH == 0, "split epilogue needs an even number of utterance groups");
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
   const int NC = a.NC;
@@ -470,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
     mbar_init(rfull + 0, 1);
     mbar_init(rfull + 1, 1);
     for (int m = 0; m < 4; m++) mbar_init(acc_full + m, 1);  // committed by the warp that issued the tile
-    mbar_init(dg_ready, 128);
+    mbar_init(dg_ready, 128 * EH);
     fence_barrier_init();
     mbar_expect_tx(rfull + 0, r_bytes);
     mbar_expect_tx(rfull + 1, r_bytes);
@@ -485,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // ---- one-time: R_slice^T -> BF16 -> tensor memory.  lane = k within the tile, column c = rows 2c, 2c+1
-  if (warp >= kIssuers) {
+  if (warp >= kIssuers && warp < kIssuers + 4) {
     const int q = warp & 3;
     const float *Rg = a.w_rec[dir];
     for (int m = 0; m < MT; m++) {
@@ -544,6 +560,8 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;
+    const int eh = (warp - kIssuers) >> 2;   // which half of the chunk's columns (split epilogue)
+    const int jb = eh * NJL;                 // my first utterance group
     const int s = lane & 3;
     const int ul = q * 8 + (lane >> 2);
     const int unit = crank * UT + ul;
@@ -551,28 +569,28 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
     float *cell = a.cell[dir];
     const bool prof = a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == kIssuers;
     long long pe[7] = {0, 0, 0, 0, 0, 0, 0};
-    float carry[NJ];  // LSTM: dc carried to the previous step; GRU: dh * z
+    float carry[NJL];  // LSTM: dc carried to the previous step; GRU: dh * z
 #pragma unroll
-    for (int j = 0; j < NJ; j++) carry[j] = 0.f;
+    for (int j = 0; j < NJL; j++) carry[j] = 0.f;
     float bsum[4] = {0.f, 0.f, 0.f, 0.f}, bsq = 0.f;  // bias gradients: sums over time and my utterances
 
     // operands of the step, prefetched kD steps ahead into rotating registers
     struct Ops {
-      float dy[NJ], g[NJ][G], c[NJ], cp[NJ];
+      float dy[NJL], g[NJL][G], c[NJL], cp[NJL];
     };
-    constexpr int kD = NJ == 1 ? 8 : 2;   // prefetch distance in steps (registers: 7 * NJ per step in flight)
+    constexpr int kD = NJL == 1 ? 8 : 2;   // prefetch distance in steps (registers: 7 * NJL per step in flight)
     Ops opsR[kD];
     auto load_step = [&](Ops &o, int step) {
-      float (&pdy)[NJ] = o.dy;
-      float (&pg)[NJ][G] = o.g;
-      float (&pc)[NJ] = o.c;
-      float (&pcp)[NJ] = o.cp;
+      float (&pdy)[NJL] = o.dy;
+      float (&pg)[NJL][G] = o.g;
+      float (&pc)[NJL] = o.c;
+      float (&pcp)[NJL] = o.cp;
       const int fstep = T - 1 - step;
       const int t = dir ? T - 1 - fstep : fstep;
       const int tp = dir ? t + 1 : t - 1;
 #pragma unroll
-      for (int j = 0; j < NJ; j++) {
-        const int b = 4 * j + s;
+      for (int j = 0; j < NJL; j++) {
+        const int b = 4 * (jb + j) + s;
         pdy[j] = 0.f;
         pc[j] = pcp[j] = 0.f;
 #pragma unroll
@@ -602,22 +620,22 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
     for (int m = 0; m < 4; m++) {
       const int tgt = 4 * m + q;
       const int ok = m < MT && tgt < NC;
-      rdst[m] = mapa_u32(smem_u32(recv) + (uint32_t)((crank * 32 + lane) * BC) * 4u, ok ? tgt : 0);
+      rdst[m] = mapa_u32(smem_u32(recv) + (uint32_t)((crank * 32 + lane) * BC + eh * BCL) * 4u, ok ? tgt : 0);
       rbar[m] = mapa_u32(smem_u32(rfull), ok ? tgt : 0);
     }
 
     auto do_step = [&](const int step, Ops &ops) {
-      float (&pdy)[NJ] = ops.dy;
-      float (&pg)[NJ][G] = ops.g;
-      float (&pc)[NJ] = ops.c;
-      float (&pcp)[NJ] = ops.cp;
+      float (&pdy)[NJL] = ops.dy;
+      float (&pg)[NJL][G] = ops.g;
+      float (&pc)[NJL] = ops.c;
+      float (&pcp)[NJL] = ops.cp;
       const int fstep = T - 1 - step;
       const int t = dir ? T - 1 - fstep : fstep;
       const int p = step & 1;
       // ---- dh arriving from the step processed before (frame t +- 1)
-      float dhr[NJ];
+      float dhr[NJL];
 #pragma unroll
-      for (int j = 0; j < NJ; j++) dhr[j] = 0.f;
+      for (int j = 0; j < NJL; j++) dhr[j] = 0.f;
       const long long c0 = prof ? clock64() : 0;
       long long c1 = c0;
       if (step > 0) {
@@ -628,9 +646,9 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
         if (warp == kIssuers && lane == 0) mbar_expect_tx(rfull + p, r_bytes);
         // all (<= 16) partial sums are loaded back to back, then added in a fixed pairwise order: a
         // rolled loop of dependent load->add pairs cost 412 cycles per step here (measured)
-        const float *rc = recv + (size_t)p * recv_floats + ul * BC + s;
+        const float *rc = recv + (size_t)p * recv_floats + ul * BC + eh * BCL + s;
 #pragma unroll
-        for (int j = 0; j < NJ; j++) {
+        for (int j = 0; j < NJL; j++) {
           float v[16];
 #pragma unroll
           for (int src = 0; src < 16; src++) v[src] = src < NC ? rc[src * 32 * BC + 4 * j] : 0.f;  // 16 loads in flight
@@ -643,9 +661,9 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
       }
       const long long c2 = prof ? clock64() : 0;
       // ---- gate gradients of (unit, batch 4j+s)
-      float dgv[NJ][4], dq[NJ];
+      float dgv[NJL][4], dq[NJL];
 #pragma unroll
-      for (int j = 0; j < NJ; j++) {
+      for (int j = 0; j < NJL; j++) {
         float dh = pdy[j] + dhr[j];
         dgv[j][0] = dgv[j][1] = dgv[j][2] = dgv[j][3] = 0.f;
         dq[j] = 0.f;
@@ -671,7 +689,7 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
           const float h = pg[j][0];
           dgv[j][0] = dh * (MODE == 0 ? (h > 0.f ? 1.f : 0.f) : (1.f - h * h));
         }
-        if (4 * j + s >= nb) {
+        if (4 * (jb + j) + s >= nb) {
           dgv[j][0] = dgv[j][1] = dgv[j][2] = dgv[j][3] = 0.f;
           dq[j] = 0.f;
           carry[j] = 0.f;
@@ -683,8 +701,8 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
       if (step + 1 < T) {
         // ---- recurrent-side gradients -> BF16 B tile [utterance row][gate row r = 4*ul + g]
 #pragma unroll
-        for (int j = 0; j < NJ; j++) {
-          const int b = 4 * j + s;
+        for (int j = 0; j < NJL; j++) {
+          const int b = 4 * (jb + j) + s;
           const float g2 = MODE == 3 ? dq[j] : dgv[j][2];
           const uint2 v = make_uint2(pack_bf16(dgv[j][0], dgv[j][1]), pack_bf16(g2, dgv[j][3]));
           const uint32_t off = (ul >> 4) * 2048 + b * 128 + ((((ul & 15) >> 1) ^ (b & 7)) << 4) + (ul & 1) * 8;
@@ -696,8 +714,8 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
       const long long c4 = prof ? clock64() : 0;
       // ---- off the critical path: gradients to HBM, operands of the next step
 #pragma unroll
-      for (int j = 0; j < NJ; j++) {
-        const int b = 4 * j + s;
+      for (int j = 0; j < NJL; j++) {
+        const int b = 4 * (jb + j) + s;
         if (b < nb) {
           const size_t row = (size_t)t * B + b_lo + b;
           float *gp = gates + row * GH + unit;
@@ -725,13 +743,13 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
               pe[0] += c1 - c0; pe[1] += c2 - c1; pe[2] += c3 - c2; pe[3] += c4 - c3; pe[4] += c5 - c4; pe[5] += c6 - c5;
             }
             tc_fence_after();
-            uint32_t r[BC];
-            tmem_ld_32xN<BC>(tmem_base + ((uint32_t)(q * 32) << 16) + m * NPAD, r);
+            uint32_t r[BCL];
+            tmem_ld_32xN<BCL>(tmem_base + ((uint32_t)(q * 32) << 16) + m * NPAD + eh * BCL, r);
             tmem_ld_wait();
             if (4 * m + q < NC) {
               const uint32_t dst = rdst[m] + (uint32_t)pn * r_bytes, bar = rbar[m] + pn * 8;
 #pragma unroll
-              for (int j = 0; j < NJ; j++) st_async_v4(dst + j * 16, r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3], bar);
+              for (int j = 0; j < NJL; j++) st_async_v4(dst + j * 16, r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3], bar);
             }
           }
         }
@@ -755,12 +773,22 @@ __global__ void __launch_bounds__(kThreads, 1) rec_tc_bwd_kernel(RecArgs a) {
       }
       bsq += __shfl_xor_sync(0xffffffffu, bsq, 1);
       bsq += __shfl_xor_sync(0xffffffffu, bsq, 2);
-      if (s == 0) {
-        float *bp = a.bias_partial + (size_t)(chunk * a.dirs + dir) * 2 * GH;
+      float *bp = a.bias_partial + (size_t)(chunk * a.dirs + dir) * 2 * GH;
+      if (s == 0 && eh == 0) {
 #pragma unroll
         for (int g = 0; g < G; g++) {
           bp[(size_t)g * H + unit] = bsum[g];                                        // input side
           bp[GH + (size_t)g * H + unit] = (MODE == 3 && g == 2) ? bsq : bsum[g];    // recurrent side
+        }
+      }
+      if (EH > 1) {  // the second set of epilogue warps adds its utterances' sums (fixed order: deterministic)
+        asm volatile("bar.sync 3, %0;" ::"n"(128 * EH) : "memory");
+        if (s == 0 && eh == 1) {
+#pragma unroll
+          for (int g = 0; g < G; g++) {
+            bp[(size_t)g * H + unit] += bsum[g];
+            bp[GH + (size_t)g * H + unit] += (MODE == 3 && g == 2) ? bsq : bsum[g];
+          }
         }
       }
     }
@@ -788,7 +816,7 @@ __global__ void bias_finalize_kernel(const float *partial, int nchunks, int dirs
 }
 
 template <typename K>
-cudaError_t launch_cluster(K kernel, const RecArgs &a, size_t smem, cudaStream_t stream) {
+cudaError_t launch_cluster(K kernel, const RecArgs &a, size_t smem, cudaStream_t stream, int threads = kThreads) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (a.NC > 8) {
@@ -798,7 +826,7 @@ cudaError_t launch_cluster(K kernel, const RecArgs &a, size_t smem, cudaStream_t
   const int nchunks = (a.B + a.BC - 1) / a.BC;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(a.NC, a.dirs * nchunks, 1);
-  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -811,6 +839,12 @@ cudaError_t launch_cluster(K kernel, const RecArgs &a, size_t smem, cudaStream_t
   return cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
+// tuning aid: B200RNN_SPLIT_EPILOGUE=0 keeps four epilogue warps at every batch chunk
+bool split_epilogue() {
+  static const bool on = !(getenv("B200RNN_SPLIT_EPILOGUE") && atoi(getenv("B200RNN_SPLIT_EPILOGUE")) == 0);
+  return on;
+}
+
 // >= 116 KB so that two CTAs never share an SM (each owns 256+ TMEM columns and an issue slot)
 constexpr size_t kSmemFloor = 116 * 1024;
 size_t fwd_smem_bytes(int H) { return std::max(kSmemFloor, 1024 + (size_t)kRingOffset + 32 * 1024); }
@@ -818,17 +852,26 @@ size_t fwd_smem_bytes(int H) { return std::max(kSmemFloor, 1024 + (size_t)kRingO
 template <int MODE>
 cudaError_t launch_fwd(const RecArgs &a, cudaStream_t stream) {
   const size_t smem = fwd_smem_bytes(a.H);
+  const bool split = split_epilogue();
   if (a.H == 320) {  // the benchmark width: K extent known at compile time
     switch (a.BC) {
-      case 4: return launch_cluster(rec_tc_fwd_kernel<MODE, 1, 5>, a, smem, stream);
-      case 8: return launch_cluster(rec_tc_fwd_kernel<MODE, 2, 5>, a, smem, stream);
-      default: return launch_cluster(rec_tc_fwd_kernel<MODE, 4, 5>, a, smem, stream);
+      case 4: return launch_cluster(rec_tc_fwd_kernel<MODE, 1, 5, 1>, a, smem, stream);
+      case 8:
+        return split ? launch_cluster(rec_tc_fwd_kernel<MODE, 2, 5, 2>, a, smem, stream, threads_of(2))
+                     : launch_cluster(rec_tc_fwd_kernel<MODE, 2, 5, 1>, a, smem, stream);
+      default:
+        return split ? launch_cluster(rec_tc_fwd_kernel<MODE, 4, 5, 2>, a, smem, stream, threads_of(2))
+                     : launch_cluster(rec_tc_fwd_kernel<MODE, 4, 5, 1>, a, smem, stream);
     }
   }
   switch (a.BC) {
-    case 4: return launch_cluster(rec_tc_fwd_kernel<MODE, 1, 0>, a, smem, stream);
-    case 8: return launch_cluster(rec_tc_fwd_kernel<MODE, 2, 0>, a, smem, stream);
-    default: return launch_cluster(rec_tc_fwd_kernel<MODE, 4, 0>, a, smem, stream);
+    case 4: return launch_cluster(rec_tc_fwd_kernel<MODE, 1, 0, 1>, a, smem, stream);
+    case 8:
+      return split ? launch_cluster(rec_tc_fwd_kernel<MODE, 2, 0, 2>, a, smem, stream, threads_of(2))
+                   : launch_cluster(rec_tc_fwd_kernel<MODE, 2, 0, 1>, a, smem, stream);
+    default:
+      return split ? launch_cluster(rec_tc_fwd_kernel<MODE, 4, 0, 2>, a, smem, stream, threads_of(2))
+                   : launch_cluster(rec_tc_fwd_kernel<MODE, 4, 0, 1>, a, smem, stream);
   }
 }
 
@@ -839,10 +882,15 @@ size_t bwd_smem_bytes(int H, int BC) {
 template <int MODE>
 cudaError_t launch_bwd(const RecArgs &a, cudaStream_t stream) {
   const size_t smem = bwd_smem_bytes(a.H, a.BC);
+  const bool split = split_epilogue();
   switch (a.BC) {
-    case 4: return launch_cluster(rec_tc_bwd_kernel<MODE, 1>, a, smem, stream);
-    case 8: return launch_cluster(rec_tc_bwd_kernel<MODE, 2>, a, smem, stream);
-    default: return launch_cluster(rec_tc_bwd_kernel<MODE, 4>, a, smem, stream);
+    case 4: return launch_cluster(rec_tc_bwd_kernel<MODE, 1, 1>, a, smem, stream);
+    case 8:
+      return split ? launch_cluster(rec_tc_bwd_kernel<MODE, 2, 2>, a, smem, stream, threads_of(2))
+                   : launch_cluster(rec_tc_bwd_kernel<MODE, 2, 1>, a, smem, stream);
+    default:
+      return split ? launch_cluster(rec_tc_bwd_kernel<MODE, 4, 2>, a, smem, stream, threads_of(2))
+                   : launch_cluster(rec_tc_bwd_kernel<MODE, 4, 1>, a, smem, stream);
   }
 }
 

@@ -106,3 +106,24 @@ def test_tensor_mode_within_stated_tolerance(mode, D, H, B, Tn):
     assert e_emul < 1e-3
     assert e_y < 5e-3
     assert e_dx < 1e-2 and e_dw < 1e-2
+
+
+@pytest.mark.parametrize("mode,H,B,bc", [(2, 64, 23, 16), (3, 128, 23, 16), (2, 320, 50, 16), (3, 64, 13, 8),
+                                         (1, 64, 21, 16)])
+def test_split_epilogue_chunks(monkeypatch, mode, H, B, bc):
+    """Batch chunks of 8 / 16 run a second set of epilogue warps (each takes half of the chunk's utterance
+    columns); ragged last chunks (23 = 16 + 7, 50 = 3 x 16 + 2, 13 = 8 + 5), all recurrent modes, and the
+    same results as four epilogue warps (B200RNN_SPLIT_EPILOGUE=0)."""
+    from oracle import pyoracle
+    D, Tn = 24, 11
+    monkeypatch.setenv("B200RNN_TC_BC", str(bc))
+    rng = np.random.default_rng(mode * 1000 + B + H)
+    n = pyoracle.rnn_param_count(mode, True, 1, D, H)
+    w = (rng.standard_normal(n) * 0.05).astype(np.float32)
+    x = rng.standard_normal((Tn * B, D)).astype(np.float32)
+    dy = rng.standard_normal((Tn * B, 2 * H)).astype(np.float32)
+    yr, dxr, dwr = pyoracle.rnn(mode, True, 1, H, x, w, B, dy=dy, dtype=np.float64)
+    y, dx, dw = _run_tc(mode, D, H, B, Tn, x, w, dy)
+    assert np.abs(y - yr).max() < 5e-3
+    assert np.abs(dx - dxr).max() / np.abs(dxr).max() < 1e-2
+    assert np.abs(dw - dwr).max() / np.abs(dwr).max() < 1e-2
