@@ -332,6 +332,32 @@ bool make_map(CUtensorMap *map, const float *base, long long inner, long long ou
   return r == CUDA_SUCCESS;
 }
 
+}  // namespace
+
+// fp32 tensor of rank 2 or 3 (dims / box innermost first; strides in elements for dims 1..rank-1), no swizzle:
+// used by the recurrent kernels to fetch [utterances x gates x 32 units] boxes with one TMA operation
+bool make_map_nd(CUtensorMap *map, const float *base, int rank, const long long *dims, const long long *strides,
+                 const int *box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn || rank < 2 || rank > 3 || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t bx[3], estr[3] = {1, 1, 1};
+  for (int i = 0; i < rank; i++) {
+    if (dims[i] <= 0 || box[i] <= 0 || box[i] > 256) return false;
+    gdim[i] = (cuuint64_t)dims[i];
+    bx[i] = (cuuint32_t)box[i];
+    if (i > 0) {
+      if (strides[i - 1] % 4) return false;
+      gstr[i - 1] = (cuuint64_t)strides[i - 1] * 4;
+    }
+  }
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float *>(base), gdim, gstr, bx, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+namespace {
+
 // Self-resetting ticket slots, handed out round-robin: a slot is reused kTicketSlots launches later,
 // long after the launch that last used it has retired (the launch queue is far shallower).
 constexpr int kTicketSlots = 2048;

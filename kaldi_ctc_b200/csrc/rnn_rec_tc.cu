@@ -28,6 +28,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "rnn_common.cuh"
 #include "tc_common.cuh"
@@ -35,9 +36,25 @@
 namespace cg = cooperative_groups;
 
 namespace b200 {
+bool make_map_nd(CUtensorMap *map, const float *base, int rank, const long long *dims, const long long *strides,
+                 const int *box);   // rnn_gemm_tc.cu
 namespace {
 
 using namespace tc;
+
+// TMA descriptors of the per-step operands (batch chunks of 8 / 16 only, see kBulk in the kernels)
+struct RecMaps {
+  CUtensorMap gates[2];   // [T*B rows][G gates][H]   box [BC][G][32]
+  CUtensorMap cell[2];    // [T*B rows][H]            box [BC][32]
+  CUtensorMap dy, y;      // [T*B rows][H*dirs]       box [BC][32]
+};
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 
 constexpr int UT = 32;          // hidden units per CTA
 constexpr int NPAD = 16;        // MMA N (utterances per chunk, zero padded)
@@ -119,7 +136,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // ===========================================================================
 // smem: [Rs: nkb x 128 rows x 128 B][hs: 2 x nkb x 16 rows x 128 B][barriers]
 template <int MODE, int NJ, int NKB, int EH>
-__global__ void __launch_bounds__(threads_of(EH), 1) rec_tc_fwd_kernel(RecArgs a) {
+__global__ void __launch_bounds__(threads_of(EH), 1)
+rec_tc_fwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
   constexpr int G = MODE == 2 ? 4 : (MODE == 3 ? 3 : 1);
   constexpr int BC = 4 * NJ;
   constexpr int NJL = NJ / EH, BCL = 4 * NJL;   // utterance groups / columns per epilogue thread
@@ -272,10 +290,30 @@ __global__ void __launch_bounds__(threads_of(EH), 1) rec_tc_fwd_kernel(RecArgs a
     // shared memory (each thread only ever reads what it copied itself, so cp.async.wait_group is the only
     // synchronisation).  Register prefetch one step ahead cost 12 % of the step at T = 2000 (HBM latency
     // tails of the slowest thread of the slowest CTA gate every step); 2 / 4 steps ahead recovered 11 / 15 %.
-    constexpr int kPF = BC == 4 ? 16 : (BC == 8 ? 8 : 4);
+    // Batch chunks of 8 / 16 (kBulk): 4-byte cp.async copies (2048 per step and CTA at 16 utterances) were
+    // 0.7 us of a 2.1 us step (LSU issue), and one 128-byte bulk copy per (utterance, gate) was worse still
+    // (64 small TMA operations per step).  There the whole [utterances x gates x my 32 units] box of a step
+    // comes with ONE 3-D TMA tile load, completion counted on one mbarrier per ring slot.
+    constexpr bool kBulk = BC >= 8;
+    constexpr int kPF = BC == 4 ? 16 : (BC == 8 ? 6 : 3);
+    constexpr int kSlotFloats = BC * G * 32;                        // kBulk slot [utterance][gate][32]: 8 KB at 16 x 4
+    float *bring = reinterpret_cast<float *>(smem + kRingOffset);
+    uint64_t *pfbar = reinterpret_cast<uint64_t *>(smem + kRingOffset - 128);   // [kPF <= 16], kBulk only
+    auto issue_bulk = [&](int step) {
+      if (step < T && !(a.dbg_flags & 2) && tid == 32 * kIssuers) {
+        const int t = dir ? T - 1 - step : step;
+        uint64_t *bar = pfbar + step % kPF;
+        mbar_expect_tx(bar, (uint32_t)kSlotFloats * 4u);
+        tma_load_3d(bring + (size_t)(step % kPF) * kSlotFloats, &tm.gates[dir], crank * UT, 0, t * B + b_lo, bar);
+      }
+    };
     // [slot][quarter thread 0..127][BC columns]; a thread owns columns [eh * BCL, eh * BCL + BCL)
     float *pring = reinterpret_cast<float *>(smem + kRingOffset) + (size_t)((tid - 32 * kIssuers) & 127) * BC + eh * BCL;
     auto issue_pre = [&](int step) {
+      if (kBulk) {
+        issue_bulk(step);
+        return;
+      }
       if (step < T && pload && !(a.dbg_flags & 2)) {
         const int t = dir ? T - 1 - step : step;
         const float *pp = gates + ((size_t)t * B + b_lo) * GH + (size_t)pcol * H + unit;
@@ -287,10 +325,18 @@ __global__ void __launch_bounds__(threads_of(EH), 1) rec_tc_fwd_kernel(RecArgs a
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    if (kBulk) {
+      if (tid == 32 * kIssuers) {
+        for (int k = 0; k < kPF; k++) mbar_init(pfbar + k, 1);
+        fence_barrier_init();
+      }
+      asm volatile("bar.sync 3, %0;" ::"n"(128 * EH) : "memory");
+    } else {
 #pragma unroll
-    for (int k = 0; k < kPF; k++) {   // slots of (thread, b) pairs that are never copied stay zero
+      for (int k = 0; k < kPF; k++) {   // slots of (thread, b) pairs that are never copied stay zero
 #pragma unroll
-      for (int b = 0; b < BCL; b++) pring[(size_t)k * 128 * BC + b] = 0.f;
+        for (int b = 0; b < BCL; b++) pring[(size_t)k * 128 * BC + b] = 0.f;
+      }
     }
     for (int k = 0; k < kPF; k++) issue_pre(k);
 
@@ -310,9 +356,14 @@ __global__ void __launch_bounds__(threads_of(EH), 1) rec_tc_fwd_kernel(RecArgs a
       const int t = dir ? T - 1 - step : step;
       const long long c0 = prof ? clock64() : 0;
       // this step's projection rows (copied kPF steps ago)
-      asm volatile("cp.async.wait_group %0;" ::"n"(kPF - 1) : "memory");
       float pre[BCL];
-      {
+      if (kBulk) {
+        if (!(a.dbg_flags & 2)) mbar_wait(pfbar + step % kPF, (uint32_t)(step / kPF) & 1u);
+        const float *ps = bring + (size_t)(step % kPF) * kSlotFloats + (eh * BCL * G + pcol) * 32 + ul;
+#pragma unroll
+        for (int b = 0; b < BCL; b++) pre[b] = (pload && !(a.dbg_flags & 2)) ? ps[b * G * 32] : 0.f;
+      } else {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kPF - 1) : "memory");
         const float *ps = pring + (size_t)(step % kPF) * 128 * BC;
 #pragma unroll
         for (int b = 0; b < BCL; b++) pre[b] = ps[b];
@@ -454,7 +505,8 @@ __global__ void __launch_bounds__(threads_of(EH), 1) rec_tc_fwd_kernel(RecArgs a
 // reduce-scatter over distributed shared memory, completion counted on the
 // peer's mbarrier.
 template <int MODE, int NJ, int EH>
-__global__ void __launch_bounds__(threads_of(EH), 1) rec_tc_bwd_kernel(RecArgs a) {
+__global__ void __launch_bounds__(threads_of(EH), 1)
+rec_tc_bwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
   constexpr int G = MODE == 2 ? 4 : (MODE == 3 ? 3 : 1);
   constexpr int BC = 4 * NJ;
   constexpr int NJL = NJ / EH, BCL = 4 * NJL;   // utterance groups / columns per epilogue thread
@@ -609,9 +661,61 @@ __global__ void __launch_bounds__(threads_of(EH), 1) rec_tc_bwd_kernel(RecArgs a
         }
       }
     };
+    // Batch chunks of 8 / 16 (kBulk): the same operands through TMA tile loads into a 3-slot ring in shared
+    // memory instead of 7 scalar loads per (thread, utterance) and step: dy [BC][32], gates [BC][G][32],
+    // c [BC][32], c_prev / h_prev [BC][32] -- three or four TMA operations per step, issued by one thread,
+    // counted on the slot's mbarrier.
+    constexpr bool kBulk = BC >= 8;
+    constexpr int kRB = 3;
+    constexpr int kOffG = BC * 32, kOffC = kOffG + BC * G * 32, kOffP = kOffC + BC * 32;
+    constexpr int kSlotFloats = kOffP + BC * 32;
+    float *oring = reinterpret_cast<float *>(smem + 4096 + 2 * (size_t)recv_floats * 4 + 256);
+    uint64_t *opbar = reinterpret_cast<uint64_t *>(smem + 4096 + 2 * (size_t)recv_floats * 4 + 128);  // [kRB]
+    auto issue_ops = [&](int step) {
+      if (tid != 32 * kIssuers) return;
+      const int fstep = T - 1 - step;
+      const int t = dir ? T - 1 - fstep : fstep;
+      const int tp = dir ? t + 1 : t - 1;
+      const bool prev = MODE >= 2 && fstep > 0;   // no previous frame at the first one
+      uint64_t *bar = opbar + step % kRB;
+      float *slot = oring + (size_t)(step % kRB) * kSlotFloats;
+      const int row = t * B + b_lo;
+      mbar_expect_tx(bar, (uint32_t)(BC * 32 * (1 + G + (MODE >= 2 ? 1 : 0) + (prev ? 1 : 0))) * 4u);
+      tma_load_2d(slot, &tm.dy, dir * H + crank * UT, row, bar);
+      tma_load_3d(slot + kOffG, &tm.gates[dir], crank * UT, 0, row, bar);
+      if (MODE >= 2) tma_load_2d(slot + kOffC, &tm.cell[dir], crank * UT, row, bar);
+      if (prev) {
+        if (MODE == 2) tma_load_2d(slot + kOffP, &tm.cell[dir], crank * UT, tp * B + b_lo, bar);
+        else tma_load_2d(slot + kOffP, &tm.y, dir * H + crank * UT, tp * B + b_lo, bar);
+      }
+    };
+    auto read_ops = [&](Ops &o, int step) {
+      mbar_wait(opbar + step % kRB, (uint32_t)(step / kRB) & 1u);
+      const bool first_frame = step == T - 1;
+      const float *slot = oring + (size_t)(step % kRB) * kSlotFloats;
 #pragma unroll
-    for (int i = 0; i < kD; i++)
-      if (i < T) load_step(opsR[i], i);
+      for (int j = 0; j < NJL; j++) {
+        const int b = 4 * (jb + j) + s;
+        o.dy[j] = slot[b * 32 + ul];
+#pragma unroll
+        for (int g = 0; g < G; g++) o.g[j][g] = slot[kOffG + (b * G + g) * 32 + ul];
+        o.c[j] = MODE >= 2 ? slot[kOffC + b * 32 + ul] : 0.f;
+        o.cp[j] = (MODE >= 2 && !first_frame) ? slot[kOffP + b * 32 + ul] : 0.f;
+      }
+    };
+    if (kBulk) {
+      if (tid == 32 * kIssuers) {
+        for (int k = 0; k < kRB; k++) mbar_init(opbar + k, 1);
+        fence_barrier_init();
+      }
+      asm volatile("bar.sync 3, %0;" ::"n"(128 * EH) : "memory");
+      for (int i = 0; i < kRB; i++)
+        if (i < T) issue_ops(i);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kD; i++)
+        if (i < T) load_step(opsR[i], i);
+    }
 
     // destination of my TMEM lanes' partial sums: for tile m, lanes of this warp are the 32
     // units of CTA 4m+q; inside its receive buffer: [parity][src = crank][lane][b]
@@ -625,6 +729,7 @@ __global__ void __launch_bounds__(threads_of(EH), 1) rec_tc_bwd_kernel(RecArgs a
     }
 
     auto do_step = [&](const int step, Ops &ops) {
+      if (kBulk) read_ops(ops, step);
       float (&pdy)[NJL] = ops.dy;
       float (&pg)[NJL][G] = ops.g;
       float (&pc)[NJL] = ops.c;
@@ -727,7 +832,7 @@ __global__ void __launch_bounds__(threads_of(EH), 1) rec_tc_bwd_kernel(RecArgs a
       }
       if (step + 1 < T) {
         // my (unit, batch) operands of later steps are not touched by anyone else: safe to prefetch now
-        if (step + kD < T) load_step(ops, step + kD);
+        if (!kBulk && step + kD < T) load_step(ops, step + kD);
         const long long c5 = prof ? clock64() : 0;
         // ---- partial dh_{prev} of my rows, for all k: scatter to the owners
         const int pn = (step + 1) & 1;
@@ -755,6 +860,9 @@ __global__ void __launch_bounds__(threads_of(EH), 1) rec_tc_bwd_kernel(RecArgs a
         }
         tc_fence_before();
         if (prof) pe[6] += clock64() - c6;
+        // every epilogue thread has arrived on dg_ready (the MMAs above needed it), i.e. is past its reads of
+        // this step's ring slot: refill it
+        if (kBulk && step + kRB < T) issue_ops(step + kRB);
       }
     };
     for (int step = 0; step < T; step += kD) {
@@ -815,8 +923,34 @@ __global__ void bias_finalize_kernel(const float *partial, int nchunks, int dirs
     }
 }
 
+// descriptors for the kBulk variants (boxes of BC utterance rows x this CTA's 32 units)
+bool make_rec_maps(const RecArgs &a, bool backward, RecMaps *m) {
+  memset(m, 0, sizeof(*m));
+  if (a.BC < 8) return true;
+  const int G = a.mode == 2 ? 4 : (a.mode == 3 ? 3 : 1);
+  const long long rows = (long long)a.T * a.B, H = a.H, HO = (long long)a.H * a.dirs;
+  for (int d = 0; d < a.dirs; d++) {
+    const long long dims3[3] = {H, G, rows}, str3[2] = {H, G * H};
+    const int box3[3] = {UT, G, a.BC};
+    if (!make_map_nd(&m->gates[d], a.gates[d], 3, dims3, str3, box3)) return false;
+    if (backward && a.mode >= 2) {
+      const long long dims2[2] = {H, rows}, str2[1] = {H};
+      const int box2[2] = {UT, a.BC};
+      if (!make_map_nd(&m->cell[d], a.cell[d], 2, dims2, str2, box2)) return false;
+    }
+  }
+  if (backward) {
+    const long long dims2[2] = {HO, rows}, str2[1] = {HO};
+    const int box2[2] = {UT, a.BC};
+    if (!make_map_nd(&m->dy, a.dy, 2, dims2, str2, box2)) return false;
+    if (a.mode == 3 && !make_map_nd(&m->y, a.y, 2, dims2, str2, box2)) return false;
+  }
+  return true;
+}
+
 template <typename K>
-cudaError_t launch_cluster(K kernel, const RecArgs &a, size_t smem, cudaStream_t stream, int threads = kThreads) {
+cudaError_t launch_cluster(K kernel, const RecArgs &a, const RecMaps &tm, size_t smem, cudaStream_t stream,
+                           int threads = kThreads) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (a.NC > 8) {
@@ -836,7 +970,7 @@ cudaError_t launch_cluster(K kernel, const RecArgs &a, size_t smem, cudaStream_t
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, a);
+  return cudaLaunchKernelEx(&cfg, kernel, a, tm);
 }
 
 // tuning aid: B200RNN_SPLIT_EPILOGUE=0 keeps four epilogue warps at every batch chunk
@@ -852,45 +986,50 @@ size_t fwd_smem_bytes(int H) { return std::max(kSmemFloor, 1024 + (size_t)kRingO
 template <int MODE>
 cudaError_t launch_fwd(const RecArgs &a, cudaStream_t stream) {
   const size_t smem = fwd_smem_bytes(a.H);
+  RecMaps tm;
+  if (!make_rec_maps(a, false, &tm)) return cudaErrorInvalidValue;
   const bool split = split_epilogue();
   if (a.H == 320) {  // the benchmark width: K extent known at compile time
     switch (a.BC) {
-      case 4: return launch_cluster(rec_tc_fwd_kernel<MODE, 1, 5, 1>, a, smem, stream);
+      case 4: return launch_cluster(rec_tc_fwd_kernel<MODE, 1, 5, 1>, a, tm, smem, stream);
       case 8:
-        return split ? launch_cluster(rec_tc_fwd_kernel<MODE, 2, 5, 2>, a, smem, stream, threads_of(2))
-                     : launch_cluster(rec_tc_fwd_kernel<MODE, 2, 5, 1>, a, smem, stream);
+        return split ? launch_cluster(rec_tc_fwd_kernel<MODE, 2, 5, 2>, a, tm, smem, stream, threads_of(2))
+                     : launch_cluster(rec_tc_fwd_kernel<MODE, 2, 5, 1>, a, tm, smem, stream);
       default:
-        return split ? launch_cluster(rec_tc_fwd_kernel<MODE, 4, 5, 2>, a, smem, stream, threads_of(2))
-                     : launch_cluster(rec_tc_fwd_kernel<MODE, 4, 5, 1>, a, smem, stream);
+        return split ? launch_cluster(rec_tc_fwd_kernel<MODE, 4, 5, 2>, a, tm, smem, stream, threads_of(2))
+                     : launch_cluster(rec_tc_fwd_kernel<MODE, 4, 5, 1>, a, tm, smem, stream);
     }
   }
   switch (a.BC) {
-    case 4: return launch_cluster(rec_tc_fwd_kernel<MODE, 1, 0, 1>, a, smem, stream);
+    case 4: return launch_cluster(rec_tc_fwd_kernel<MODE, 1, 0, 1>, a, tm, smem, stream);
     case 8:
-      return split ? launch_cluster(rec_tc_fwd_kernel<MODE, 2, 0, 2>, a, smem, stream, threads_of(2))
-                   : launch_cluster(rec_tc_fwd_kernel<MODE, 2, 0, 1>, a, smem, stream);
+      return split ? launch_cluster(rec_tc_fwd_kernel<MODE, 2, 0, 2>, a, tm, smem, stream, threads_of(2))
+                   : launch_cluster(rec_tc_fwd_kernel<MODE, 2, 0, 1>, a, tm, smem, stream);
     default:
-      return split ? launch_cluster(rec_tc_fwd_kernel<MODE, 4, 0, 2>, a, smem, stream, threads_of(2))
-                   : launch_cluster(rec_tc_fwd_kernel<MODE, 4, 0, 1>, a, smem, stream);
+      return split ? launch_cluster(rec_tc_fwd_kernel<MODE, 4, 0, 2>, a, tm, smem, stream, threads_of(2))
+                   : launch_cluster(rec_tc_fwd_kernel<MODE, 4, 0, 1>, a, tm, smem, stream);
   }
 }
 
 size_t bwd_smem_bytes(int H, int BC) {
-  return std::max(kSmemFloor, 1024 + 4096 + (size_t)2 * (H / UT) * 32 * BC * 4 + 128);
+  const size_t ring = BC >= 8 ? 256 + (size_t)3 * BC * 7 * 32 * 4 : 128;   // operand ring of the TMA variant
+  return std::max(kSmemFloor, 1024 + 4096 + (size_t)2 * (H / UT) * 32 * BC * 4 + ring);
 }
 
 template <int MODE>
 cudaError_t launch_bwd(const RecArgs &a, cudaStream_t stream) {
   const size_t smem = bwd_smem_bytes(a.H, a.BC);
+  RecMaps tm;
+  if (!make_rec_maps(a, true, &tm)) return cudaErrorInvalidValue;
   const bool split = split_epilogue();
   switch (a.BC) {
-    case 4: return launch_cluster(rec_tc_bwd_kernel<MODE, 1, 1>, a, smem, stream);
+    case 4: return launch_cluster(rec_tc_bwd_kernel<MODE, 1, 1>, a, tm, smem, stream);
     case 8:
-      return split ? launch_cluster(rec_tc_bwd_kernel<MODE, 2, 2>, a, smem, stream, threads_of(2))
-                   : launch_cluster(rec_tc_bwd_kernel<MODE, 2, 1>, a, smem, stream);
+      return split ? launch_cluster(rec_tc_bwd_kernel<MODE, 2, 2>, a, tm, smem, stream, threads_of(2))
+                   : launch_cluster(rec_tc_bwd_kernel<MODE, 2, 1>, a, tm, smem, stream);
     default:
-      return split ? launch_cluster(rec_tc_bwd_kernel<MODE, 4, 2>, a, smem, stream, threads_of(2))
-                   : launch_cluster(rec_tc_bwd_kernel<MODE, 4, 1>, a, smem, stream);
+      return split ? launch_cluster(rec_tc_bwd_kernel<MODE, 4, 2>, a, tm, smem, stream, threads_of(2))
+                   : launch_cluster(rec_tc_bwd_kernel<MODE, 4, 1>, a, tm, smem, stream);
   }
 }
 
