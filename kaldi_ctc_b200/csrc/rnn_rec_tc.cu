@@ -525,7 +525,7 @@ rec_tc_bwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   uint8_t *dgs = smem;                                              // 2 k-blocks x [16 rows x 128 B]
-  float *recv = reinterpret_cast<float *>(smem + 4096);            // [2][NC][32][BC]
+  float *recv = reinterpret_cast<float *>(smem + 4096);            // [2][NC][BC/4 groups][32 units][4 utterances]
   const int recv_floats = NC * 32 * BC;
   uint64_t *rfull = reinterpret_cast<uint64_t *>(smem + 4096 + 2 * recv_floats * 4);  // [2]
   uint64_t *acc_full = rfull + 2;          // [4]: one per M tile, so a tile can leave while the next computes
@@ -666,10 +666,12 @@ rec_tc_bwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
     // c [BC][32], c_prev / h_prev [BC][32] -- three or four TMA operations per step, issued by one thread,
     // counted on the slot's mbarrier.
     constexpr bool kBulk = BC >= 8;
+    constexpr bool kBulkRS = BC >= 16;   // bulk-copy reduce-scatter (measured slower than st.async at 8 utterances)
     constexpr int kRB = 3;
     constexpr int kOffG = BC * 32, kOffC = kOffG + BC * G * 32, kOffP = kOffC + BC * 32;
     constexpr int kSlotFloats = kOffP + BC * 32;
     float *oring = reinterpret_cast<float *>(smem + 4096 + 2 * (size_t)recv_floats * 4 + 256);
+    float *stage = oring + kRB * kSlotFloats;   // [epilogue warp][M tile][NJL x 32 units x 4 slots]: outgoing partial sums
     uint64_t *opbar = reinterpret_cast<uint64_t *>(smem + 4096 + 2 * (size_t)recv_floats * 4 + 128);  // [kRB]
     auto issue_ops = [&](int step) {
       if (tid != 32 * kIssuers) return;
@@ -724,7 +726,9 @@ rec_tc_bwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
     for (int m = 0; m < 4; m++) {
       const int tgt = 4 * m + q;
       const int ok = m < MT && tgt < NC;
-      rdst[m] = mapa_u32(smem_u32(recv) + (uint32_t)((crank * 32 + lane) * BC + eh * BCL) * 4u, ok ? tgt : 0);
+      // receive layout [src][utterance group][unit][slot]: a reading warp's 8 units x 4 slots are 32 consecutive
+      // floats (with [src][unit][utterance] the reads were 4-way bank-conflicted at 16 utterances: 820 cycles per step)
+      rdst[m] = mapa_u32(smem_u32(recv) + (uint32_t)(((crank * NJ + jb) * 32 + lane) * 4) * 4u, ok ? tgt : 0);
       rbar[m] = mapa_u32(smem_u32(rfull), ok ? tgt : 0);
     }
 
@@ -751,12 +755,12 @@ rec_tc_bwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
         if (warp == kIssuers && lane == 0) mbar_expect_tx(rfull + p, r_bytes);
         // all (<= 16) partial sums are loaded back to back, then added in a fixed pairwise order: a
         // rolled loop of dependent load->add pairs cost 412 cycles per step here (measured)
-        const float *rc = recv + (size_t)p * recv_floats + ul * BC + eh * BCL + s;
+        const float *rc = recv + (size_t)p * recv_floats + (jb * 32 + ul) * 4 + s;
 #pragma unroll
         for (int j = 0; j < NJL; j++) {
           float v[16];
 #pragma unroll
-          for (int src = 0; src < 16; src++) v[src] = src < NC ? rc[src * 32 * BC + 4 * j] : 0.f;  // 16 loads in flight
+          for (int src = 0; src < 16; src++) v[src] = src < NC ? rc[src * 32 * BC + j * 128] : 0.f;  // 16 loads in flight
 #pragma unroll
           for (int w2 = 8; w2 >= 1; w2 >>= 1)   // fixed-order tree: deterministic
 #pragma unroll
@@ -839,6 +843,10 @@ rec_tc_bwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
         long long c6 = c5;
         // tile by tile (each issued and committed by its own warp):
         // the partial sums of an early tile are in flight while the later tiles still compute
+        if (kBulkRS) {   // last step's bulk copies have long read their staging area; make it formal
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
 #pragma unroll
         for (int m = 0; m < 4; m++) {
           if (m < MT) {
@@ -853,8 +861,30 @@ rec_tc_bwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
             tmem_ld_wait();
             if (4 * m + q < NC) {
               const uint32_t dst = rdst[m] + (uint32_t)pn * r_bytes, bar = rbar[m] + pn * 8;
+              if (kBulkRS) {
+                // 16 utterances: 1536 st.async per step and CTA (one mbarrier update each at the receiver) cost
+                // ~1200 cycles per step.  My warp's part of peer 4m+q's block is contiguous there
+                // ([group][unit][slot]): park it in shared memory and send it as ONE bulk copy.
+                float4 *st4 = reinterpret_cast<float4 *>(stage) + ((warp - kIssuers) * 4 + m) * NJL * 32;
 #pragma unroll
-              for (int j = 0; j < NJL; j++) st_async_v4(dst + j * 16, r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3], bar);
+                for (int j = 0; j < NJL; j++)
+                  st4[j * 32 + lane] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                  asm volatile(
+                      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                          dst),
+                      "r"(smem_u32(st4)), "n"(NJL * 512), "r"(bar)
+                      : "memory");
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < NJL; j++)
+                  st_async_v4(dst + j * 512, r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3], bar);
+              }
             }
           }
         }
@@ -1012,7 +1042,8 @@ cudaError_t launch_fwd(const RecArgs &a, cudaStream_t stream) {
 }
 
 size_t bwd_smem_bytes(int H, int BC) {
-  const size_t ring = BC >= 8 ? 256 + (size_t)3 * BC * 7 * 32 * 4 : 128;   // operand ring of the TMA variant
+  // operand ring of the TMA variant + staging of the outgoing partial sums (8 warps x 4 tiles x BC/8 x 512 B)
+  const size_t ring = BC >= 8 ? 256 + (size_t)3 * BC * 7 * 32 * 4 + (size_t)32 * (BC / 8) * 512 : 128;
   return std::max(kSmemFloor, 1024 + 4096 + (size_t)2 * (H / UT) * 32 * BC * 4 + ring);
 }
 
