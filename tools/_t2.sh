@@ -1,4 +1,5 @@
-timeout 600 python -m pytest tests/test_rnn_tc_gpu.py tests/test_train_step_gpu.py -x -q 2>&1 | tail -3
-python tools/rnn_time.py tensor 2000 32 640 320 2 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('B32 lstm fwd us/step', round(d['us_per_step_fwd_rec'],3), 'bwd', round(d['us_per_step_bwd_rec'],3))"
-B200RNN_TC_PROFILE=1 python tools/rnn_time.py tensor 2000 64 640 320 2 2>&1 | grep "b200rnn" | tail -5 | cut -c1-330
-python tools/step_time.py 2>&1 | tail -8
+python -m pytest tests -m gpu -x -q > gpurun_out/s4_pytest.log 2>&1; tail -3 gpurun_out/s4_pytest.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+python bench.py --steps 5 --warmup 3 > gpurun_out/s4_bench.json 2> gpurun_out/s4_bench.err; python -c "
+import json; d=json.loads(open('gpurun_out/s4_bench.json').read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['ctc_roofline']['frac'], d['ctc_roofline']['ms_per_call'], d['roofline']['frac'], d['gpu_launches'])"
+python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | cut -c1-300
