@@ -143,6 +143,10 @@ rec_tc_fwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
   constexpr int NJL = NJ / EH, BCL = 4 * NJL;   // utterance groups / columns per epilogue thread
   constexpr int kThreads = threads_of(EH);
   static_assert(NJ % EH == 0, "split epilogue needs an even number of utterance groups");
+  // 16 utterances: the h tile is laid out in 64-byte-swizzle k-blocks of 32 units, so that one CTA's slice
+  // ([16 rows][64 B] = 1 KB) is contiguous in every peer's tile and travels as ONE bulk DSMEM copy per peer
+  // instead of 1024 st.async per step and CTA (one mbarrier update each at the receiver: 788 cycles per step)
+  constexpr bool kSW64 = BC >= 16;
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
   const int NC = a.NC;
@@ -232,19 +236,21 @@ rec_tc_fwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
         // warp-uniform issue: every lane computes the (uniform) descriptors, one elected lane
         // issues -- keeps the operands in uniform registers (no per-MMA R2UR/ELECT loop)
         // descriptor of the first K slice; later slices only add to the 14-bit address field
-        const uint64_t bd0 = smem_desc(hs0 + p * hs_bytes, 0, 1024, kLayoutSw128);
+        const uint64_t bd0 = smem_desc(hs0 + p * hs_bytes, 0, kSW64 ? 512 : 1024, kSW64 ? kLayoutSw64 : kLayoutSw128);
         const uint32_t dacc = tmem_d + warp * NPAD;
         if (NKB > 0) {
 #pragma unroll
           for (int i = 0; i < NKB; i++) {
             const int kk = kIssuers * i + warp;  // K slices interleaved over the issuing warps
-            const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * 2048 + (kk & 3) * 32) >> 4);
+            const uint64_t bd = bd0 + (uint64_t)((kSW64 ? (kk >> 1) * 1024 + (kk & 1) * 32
+                                                        : (kk >> 2) * 2048 + (kk & 3) * 32) >> 4);
             if (elect_one()) mma_bf16_ts(dacc, tmem_d + kACol + kk * 8, bd, idesc, i ? 1u : 0u);
           }
         } else {
           for (int i = 0; i < nkb; i++) {
             const int kk = kIssuers * i + warp;
-            const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * 2048 + (kk & 3) * 32) >> 4);
+            const uint64_t bd = bd0 + (uint64_t)((kSW64 ? (kk >> 1) * 1024 + (kk & 1) * 32
+                                                        : (kk >> 2) * 2048 + (kk & 3) * 32) >> 4);
             if (elect_one()) mma_bf16_ts(dacc, tmem_d + kACol + kk * 8, bd, idesc, i ? 1u : 0u);
           }
         }
@@ -348,6 +354,9 @@ rec_tc_fwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
     const uint32_t rhs_b = mapa_u32(smem_u32(hs), peer_b < NC ? peer_b : 0);
     const uint32_t rhf_a = mapa_u32(smem_u32(hfull), peer_a < NC ? peer_a : 0);
     const uint32_t rhf_b = mapa_u32(smem_u32(hfull), peer_b < NC ? peer_b : 0);
+    const uint32_t rhs_l = mapa_u32(smem_u32(hs), lane < NC ? lane : 0);       // kSW64: lane i -> CTA i
+    const uint32_t rhf_l = mapa_u32(smem_u32(hfull), lane < NC ? lane : 0);
+    uint8_t *hstage = smem + kRingOffset + 32 * 1024;                          // kSW64: [2][16 rows][64 B]
 
     const bool prof = a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == kIssuers;
     long long pe[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -447,9 +456,30 @@ rec_tc_fwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
           if (lane & 16) ch = make_uint4(lo2, hi2, lo, hi);
           else ch = make_uint4(lo, hi, lo2, hi2);
           const int b = 4 * (jb + j) + s;
-          const uint32_t off = pn * hs_bytes + kb_mine * 2048 + b * 128 + ((chunk_mine ^ (b & 7)) << 4);
-          if (peer_a < NC) st_async_v4(rhs_a + off, ch.x, ch.y, ch.z, ch.w, rhf_a + pn * 8);
-          if (peer_b < NC) st_async_v4(rhs_b + off, ch.x, ch.y, ch.z, ch.w, rhf_b + pn * 8);
+          if (kSW64) {   // my slice of the tile, in the peers' (64-byte swizzle) layout, into local staging
+            if ((lane >> 2) == 0)
+              *reinterpret_cast<uint4 *>(hstage + pn * 1024 + b * 64 + ((q ^ ((b >> 1) & 3)) << 4)) = ch;
+          } else {
+            const uint32_t off = pn * hs_bytes + kb_mine * 2048 + b * 128 + ((chunk_mine ^ (b & 7)) << 4);
+            if (peer_a < NC) st_async_v4(rhs_a + off, ch.x, ch.y, ch.z, ch.w, rhf_a + pn * 8);
+            if (peer_b < NC) st_async_v4(rhs_b + off, ch.x, ch.y, ch.z, ch.w, rhf_b + pn * 8);
+          }
+        }
+        if (kSW64) {
+          fence_proxy_async();
+          const bool sender = warp == kIssuers && lane < NC;   // lane i ships the slice to CTA i
+          // the copy of the previous step has read the other buffer; it (and all older ones) is done before
+          // anyone passes the barrier, i.e. before the buffer it used is written again at the next step
+          if (sender) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 3, %0;" ::"n"(128 * EH) : "memory");
+          if (sender) {
+            asm volatile(
+                "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    rhs_l + (uint32_t)(pn * hs_bytes + crank * 1024)),
+                "r"(smem_u32(hstage + pn * 1024)), "n"(BC * 64), "r"(rhf_l + pn * 8)
+                : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
         }
         if (prof) c4 = c5 = c6 = clock64();
       }
@@ -1011,7 +1041,8 @@ bool split_epilogue() {
 
 // >= 116 KB so that two CTAs never share an SM (each owns 256+ TMEM columns and an issue slot)
 constexpr size_t kSmemFloor = 116 * 1024;
-size_t fwd_smem_bytes(int H) { return std::max(kSmemFloor, 1024 + (size_t)kRingOffset + 32 * 1024); }
+// h tiles + barriers | operand ring (32 KB) | staging of the outgoing h slice (2 KB, 16 utterances)
+size_t fwd_smem_bytes(int H) { return std::max(kSmemFloor, 1024 + (size_t)kRingOffset + 32 * 1024 + 2048); }
 
 template <int MODE>
 cudaError_t launch_fwd(const RecArgs &a, cudaStream_t stream) {

@@ -157,6 +157,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 constexpr uint32_t kLayoutSw128 = 2;         // 128-byte swizzle of 16-byte chunks  (Swizzle<3,4,3>)
+constexpr uint32_t kLayoutSw64 = 4;          // 64-byte swizzle of 16-byte chunks   (Swizzle<2,4,3>)
 constexpr uint32_t kLayoutSw128Base32 = 1;   // 128-byte swizzle of 32-byte chunks  (Swizzle<2,5,2>):
                                              // the only layout for MN-major 32-bit (tf32) operands
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
