@@ -78,6 +78,7 @@ struct CtcDev {
   const int *uniq_lab;    // per utt: distinct labels (ascending)
   const int *uniq_start;  // per utt: nuniq+1 offsets into pos
   const int *pos;         // per utt: label positions grouped by label
+  const int *nuniq;       // [B] number of distinct labels (uploaded with the CSR, after K1/K2 are queued)
   float *lse2;            // [Tmax*B] base-2 log-sum-exp of each row
   float *E;
   float *alpha;
@@ -564,7 +565,8 @@ __global__ void __launch_bounds__(kK3Warps * 32) ctc_grad_kernel(CtcDev d, int s
   if (lane == 0) g[d.blank] = gs * (ex2_approx(__ldg(a + d.blank) * kLog2e - l2) - zb * invZ);
   // overwrite the entries of the labels that occur.  Per-label posterior mass from shared memory in a
   // fixed order (deterministic); the activation gathers are L2 hits, four independent ones in flight.
-  for (int j0 = lane; j0 < um.nuniq; j0 += 128) {
+  const int nuniq = __ldg(d.nuniq + b);
+  for (int j0 = lane; j0 < nuniq; j0 += 128) {
     int kk[4];
     float vv[4], mass[4];
 #pragma unroll
@@ -572,7 +574,7 @@ __global__ void __launch_bounds__(kK3Warps * 32) ctc_grad_kernel(CtcDev d, int s
       const int j = j0 + 32 * i;
       kk[i] = d.blank;
       mass[i] = 0.f;
-      if (j < um.nuniq) {
+      if (j < nuniq) {
         kk[i] = __ldg(ul + j);
         const int q1 = __ldg(us + j + 1);
         for (int q = __ldg(us + j); q < q1; q++) mass[i] += sm[__ldg(pos + q)];
@@ -582,7 +584,7 @@ __global__ void __launch_bounds__(kK3Warps * 32) ctc_grad_kernel(CtcDev d, int s
     for (int i = 0; i < 4; i++) vv[i] = __ldg(a + kk[i]);
 #pragma unroll
     for (int i = 0; i < 4; i++)
-      if (j0 + 32 * i < um.nuniq) g[kk[i]] = gs * (ex2_approx(vv[i] * kLog2e - l2) - mass[i] * invZ);
+      if (j0 + 32 * i < nuniq) g[kk[i]] = gs * (ex2_approx(vv[i] * kLog2e - l2) - mass[i] * invZ);
   }
 }
 
@@ -735,7 +737,7 @@ __global__ void __launch_bounds__(kRingThreads, 2) ctc_grad_ring_kernel(CtcDev d
       if (cur.b != loaded_b) {  // new utterance: its label -> positions CSR into shared memory
         named_bar_sync(1, kRingConsumers);
         const UttMeta um = d.meta[cur.b];
-        nuniq = um.nuniq;
+        nuniq = d.nuniq[cur.b];
         const int *ul = d.uniq_lab + um.csr_off, *us = d.uniq_start + um.csr_off + cur.b, *pos = d.pos + um.lab_off;
         for (int k = tid; k <= nuniq; k += kRingConsumers) s_us[k] = us[k];
         for (int k = tid; k < nuniq; k += kRingConsumers) s_ul[k] = ul[k];
@@ -852,7 +854,7 @@ __global__ void __launch_bounds__(kRingThreads, 2) ctc_grad_ring_kernel(CtcDev d
 struct Plan {
   int A, B, Tmax, maxL, pitch_max;
   long long sumT, sumL;
-  size_t off_meta, off_labels, off_uniq_lab, off_uniq_start, off_pos;  // header block
+  size_t off_meta, off_labels, off_uniq_lab, off_uniq_start, off_pos, off_nuniq;  // header block
   size_t header_bytes;
   size_t off_lse2, off_E, off_alpha, off_beta, off_offA, off_offB, off_logp2, off_costs, off_flags;
   size_t total;
@@ -898,6 +900,7 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int A,
   p->off_uniq_lab = o;    o = align_up(o + sizeof(int) * (p->sumL + 1), 256);
   p->off_uniq_start = o;  o = align_up(o + sizeof(int) * (p->sumL + B + 1), 256);
   p->off_pos = o;         o = align_up(o + sizeof(int) * (p->sumL + 1), 256);
+  p->off_nuniq = o;       o = align_up(o + sizeof(int) * B, 256);
   p->header_bytes = o;
   p->off_lse2 = o;   o = align_up(o + sizeof(float) * (size_t)p->Tmax * B, 256);
   p->off_E = o;      o = align_up(o + sizeof(float) * (size_t)e_off, 256);
@@ -919,6 +922,8 @@ struct Staging {
   size_t cap = 0;
   float *costs = nullptr;
   size_t costs_cap = 0;
+  cudaEvent_t copied = nullptr;   // recorded after the last upload out of `pinned`
+  bool pending = false;
 };
 Staging g_stage;
 
@@ -977,14 +982,16 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   int *hul = reinterpret_cast<int *>(h + p.off_uniq_lab);
   int *hus = reinterpret_cast<int *>(h + p.off_uniq_start);
   int *hpos = reinterpret_cast<int *>(h + p.off_pos);
-  // label -> states CSR in O(L) per utterance: groups in order of first appearance, positions
-  // ascending inside a group (a fixed summation order => deterministic gradients)
-  static thread_local std::vector<int> stamp, slot, cnt;
-  if ((int)stamp.size() < A) {
-    stamp.assign(A, -1);
-    slot.assign(A, 0);
+  int *hnu = reinterpret_cast<int *>(h + p.off_nuniq);
+  // the previous call's uploads out of the pinned block may still be queued (no_sync callers): wait for them
+  if (!g_stage.copied && cudaEventCreateWithFlags(&g_stage.copied, cudaEventDisableTiming) != cudaSuccess)
+    return CTC_STATUS_MEMOPS_FAILED;
+  if (g_stage.pending) {
+    cudaEventSynchronize(g_stage.copied);
+    g_stage.pending = false;
   }
-  static thread_local int epoch = 0;
+  // ---- stage 1: what K1 and K2 need (lengths, offsets, labels, feasibility) -> device, kernels queued;
+  //      stage 2 (below, while those kernels run): the label -> positions CSR that only K3 reads
   long long vrows_total = 0;
   for (int b = 0; b < B; b++) {
     UttMeta &m = p.meta[b];
@@ -996,38 +1003,59 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
       hl[m.lab_off + i] = lab[i];
     }
     m.feasible = (m.L + repeats <= m.T) ? 1 : 0;
-    ++epoch;
-    int nu = 0;
-    int *us = hus + m.csr_off + b;
-    cnt.assign(m.L + 1, 0);
-    for (int i = 0; i < m.L; i++) {
-      const int k = lab[i];
-      if (stamp[k] != epoch) {
-        stamp[k] = epoch;
-        slot[k] = nu;
-        hul[m.csr_off + nu] = k;
-        nu++;
-      }
-      cnt[slot[k]]++;
-    }
-    int run_ = 0;
-    for (int j = 0; j < nu; j++) {
-      us[j] = run_;
-      run_ += cnt[j];
-      cnt[j] = us[j];  // becomes the write cursor of group j
-    }
-    us[nu] = m.L;
-    for (int i = 0; i < m.L; i++) hpos[m.lab_off + cnt[slot[lab[i]]]++] = i;
-    m.nuniq = nu;
+    m.nuniq = 0;  // (device code reads CtcDev::nuniq)
     m.vrow0 = vrows_total;
     if (m.feasible) vrows_total += m.T;
     hm[b] = m;
   }
   unsigned char *w = static_cast<unsigned char *>(workspace);
-  if (cudaMemcpyAsync(w, h, p.header_bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess)
+  if (cudaMemcpyAsync(w, h, p.off_uniq_lab, cudaMemcpyHostToDevice, stream) != cudaSuccess)
     return CTC_STATUS_MEMOPS_FAILED;
   if (cudaMemsetAsync(w + p.off_costs, 0, (p.off_flags + 256) - p.off_costs, stream) != cudaSuccess)
     return CTC_STATUS_MEMOPS_FAILED;
+  // label -> states CSR in O(L) per utterance: groups in order of first appearance, positions
+  // ascending inside a group (a fixed summation order => deterministic gradients)
+  auto build_and_upload_csr = [&]() -> bool {
+    static thread_local std::vector<int> stamp, slot, cnt;
+    if ((int)stamp.size() < A) {
+      stamp.assign(A, -1);
+      slot.assign(A, 0);
+    }
+    static thread_local int epoch = 0;
+    for (int b = 0; b < B; b++) {
+      const UttMeta &m = p.meta[b];
+      const int *lab = flat_labels + m.lab_off;
+      ++epoch;
+      int nu = 0;
+      int *us = hus + m.csr_off + b;
+      cnt.assign(m.L + 1, 0);
+      for (int i = 0; i < m.L; i++) {
+        const int k = lab[i];
+        if (stamp[k] != epoch) {
+          stamp[k] = epoch;
+          slot[k] = nu;
+          hul[m.csr_off + nu] = k;
+          nu++;
+        }
+        cnt[slot[k]]++;
+      }
+      int run_ = 0;
+      for (int j = 0; j < nu; j++) {
+        us[j] = run_;
+        run_ += cnt[j];
+        cnt[j] = us[j];  // becomes the write cursor of group j
+      }
+      us[nu] = m.L;
+      for (int i = 0; i < m.L; i++) hpos[m.lab_off + cnt[slot[lab[i]]]++] = i;
+      hnu[b] = nu;
+    }
+    if (cudaMemcpyAsync(w + p.off_uniq_lab, h + p.off_uniq_lab, p.header_bytes - p.off_uniq_lab,
+                        cudaMemcpyHostToDevice, stream) != cudaSuccess)
+      return false;
+    cudaEventRecord(g_stage.copied, stream);
+    g_stage.pending = true;
+    return true;
+  };
 
   CtcDev dev;
   dev.act = act;
@@ -1042,6 +1070,7 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   dev.uniq_lab = reinterpret_cast<const int *>(w + p.off_uniq_lab);
   dev.uniq_start = reinterpret_cast<const int *>(w + p.off_uniq_start);
   dev.pos = reinterpret_cast<const int *>(w + p.off_pos);
+  dev.nuniq = reinterpret_cast<const int *>(w + p.off_nuniq);
   dev.lse2 = reinterpret_cast<float *>(w + p.off_lse2);
   dev.E = reinterpret_cast<float *>(w + p.off_E);
   dev.alpha = reinterpret_cast<float *>(w + p.off_alpha);
@@ -1184,6 +1213,12 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
     if (ngroups > 1) cudaEventRecord(e2[gi], st);
   }
   if (prof) cudaEventRecord(ev[2], stream);
+  if (grad) {
+    if (!build_and_upload_csr()) return CTC_STATUS_MEMOPS_FAILED;   // host work under the kernels queued above
+  } else {
+    cudaEventRecord(g_stage.copied, stream);
+    g_stage.pending = true;
+  }
   for (int gi = 0; gi < ngroups; gi++) {  // K3
     const long long rows = set_group(gi);
     if (ngroups > 1) cudaStreamWaitEvent(stream, e2[gi], 0);  // (also joins the side stream back)
