@@ -299,8 +299,10 @@ rec_tc_fwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
     // Batch chunks of 8 / 16 (kBulk): 4-byte cp.async copies (2048 per step and CTA at 16 utterances) were
     // 0.7 us of a 2.1 us step (LSU issue), and one 128-byte bulk copy per (utterance, gate) was worse still
     // (64 small TMA operations per step).  There the whole [utterances x gates x my 32 units] box of a step
-    // comes with ONE 3-D TMA tile load, completion counted on one mbarrier per ring slot.
-    constexpr bool kBulk = BC >= 8;
+    // comes with ONE 3-D TMA tile load, completion counted on one mbarrier per ring slot.  At 4 utterances the
+    // same tile load (2 KB boxes, 16 slots) replaces the cp.async ring as well: 0.772 -> 0.750 us per step
+    // (kBulk = false keeps the cp.async variant for comparison).
+    constexpr bool kBulk = true;
     constexpr int kPF = BC == 4 ? 16 : (BC == 8 ? 6 : 3);
     constexpr int kSlotFloats = BC * G * 32;                        // kBulk slot [utterance][gate][32]: 8 KB at 16 x 4
     float *bring = reinterpret_cast<float *>(smem + kRingOffset);
@@ -695,7 +697,7 @@ rec_tc_bwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
     // memory instead of 7 scalar loads per (thread, utterance) and step: dy [BC][32], gates [BC][G][32],
     // c [BC][32], c_prev / h_prev [BC][32] -- three or four TMA operations per step, issued by one thread,
     // counted on the slot's mbarrier.
-    constexpr bool kBulk = BC >= 8;
+    constexpr bool kBulk = BC >= 8;      // (at 4 utterances the rotating registers win: 0.78 vs 0.84 us per step)
     constexpr bool kBulkRS = BC >= 16;   // bulk-copy reduce-scatter (measured slower than st.async at 8 utterances)
     constexpr int kRB = 3;
     constexpr int kOffG = BC * 32, kOffC = kOffG + BC * G * 32, kOffP = kOffC + BC * 32;
@@ -986,7 +988,7 @@ __global__ void bias_finalize_kernel(const float *partial, int nchunks, int dirs
 // descriptors for the kBulk variants (boxes of BC utterance rows x this CTA's 32 units)
 bool make_rec_maps(const RecArgs &a, bool backward, RecMaps *m) {
   memset(m, 0, sizeof(*m));
-  if (a.BC < 8) return true;
+  if (a.BC < 8 && backward) return true;   // the backward kernel keeps its register prefetch at 4 utterances
   const int G = a.mode == 2 ? 4 : (a.mode == 3 ? 3 : 1);
   const long long rows = (long long)a.T * a.B, H = a.H, HO = (long long)a.H * a.dirs;
   for (int d = 0; d < a.dirs; d++) {
