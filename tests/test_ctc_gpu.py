@@ -221,3 +221,23 @@ def test_argmax_written_for_infeasible_utterances_too(ctx):
     op.compute_extended(a, fl, ll, il, gradients=torch.empty_like(a), argmax_dev=am)
     torch.cuda.synchronize()
     assert np.array_equal(am.cpu().numpy().reshape(4, 2), act.argmax(2))
+
+
+def test_wide_alphabet_default_path_properties(ctx):
+    """A slab large enough (154 MB) that the library picks the persistent TMA-ring gradient kernel and two
+    utterance groups by itself: parity with the fp64 oracle, gradient rows sum to zero, padded rows are exactly
+    zero, and two calls give bit-identical results (fixed summation orders everywhere)."""
+    from kaldi_ctc_b200 import synth
+    from oracle import pyoracle
+    bt = synth.ctc_batch(16, 4000, 300, 600, 50, 280, seed=77, sigma=2.0)
+    costs, grad = _run(ctx, bt.activations, bt.flat_labels, bt.label_lengths, bt.input_lengths)
+    costs2, grad2 = _run(ctx, bt.activations, bt.flat_labels, bt.label_lengths, bt.input_lengths)
+    np.testing.assert_array_equal(costs, costs2)
+    np.testing.assert_array_equal(grad, grad2)
+    assert np.all(np.isfinite(costs))
+    assert np.abs(grad.sum(-1)).max() < 1e-4
+    for b, Tb in enumerate(bt.input_lengths):
+        assert np.all(grad[Tb:, b, :] == 0)
+    c_ref, g_ref = pyoracle.ctc(bt.activations, bt.flat_labels, bt.label_lengths, bt.input_lengths,
+                                dtype=np.float64)
+    _check(costs, grad, c_ref, g_ref)
