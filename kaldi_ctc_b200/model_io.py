@@ -7,6 +7,7 @@ the CTC topology, and the <FilterParams> blob <-> PyTorch parameter order.
   ClipGradientComponent::Write           src/nnet2/nnet-cudnn-component.cc:814-837
   AffineComponent::Write                 src/nnet2/nnet-component.cc:1260-1274
   NonlinearComponent::Write (Softmax)    src/nnet2/nnet-component.cc:398-412
+  SpliceComponent::Write                 src/nnet2/nnet-component.cc:2822-2831
   basic types / vectors / matrices       src/base/io-funcs.cc:26-75, matrix/kaldi-vector.cc:1202-1222,
                                          matrix/kaldi-matrix.cc:1213-1245
 
@@ -84,6 +85,18 @@ def _r_bool(is_):
     return c == b"T"
 
 
+def _w_ivec(os, v):  # WriteIntegerVector<int32>, base/io-funcs-inl.h:198-211
+    v = np.ascontiguousarray(v, dtype="<i4").reshape(-1)
+    os.write(b"\x04" + struct.pack("<i", v.size) + v.tobytes())
+
+
+def _r_ivec(is_):
+    if is_.read(1) != b"\x04":
+        raise ValueError("ReadIntegerVector: expected 4-byte elements")
+    n = struct.unpack("<i", is_.read(4))[0]
+    return np.frombuffer(is_.read(4 * n), dtype="<i4").copy()
+
+
 def _w_vec(os, v, dtype="<f4"):
     v = np.ascontiguousarray(v, dtype=dtype).reshape(-1)
     _tok(os, "FV" if dtype == "<f4" else "DV")
@@ -148,6 +161,10 @@ def _write_component(os, c):
         _tok(os, "<LinearParams>"); _w_mat(os, c["linear_params"])
         _tok(os, "<BiasParams>"); _w_vec(os, c["bias_params"])
         _tok(os, "<IsGradient>"); _w_bool(os, c.get("is_gradient", False))
+    elif t == "SpliceComponent":
+        _tok(os, "<InputDim>"); _w_i32(os, c["input_dim"])
+        _tok(os, "<Context>"); _w_ivec(os, c["context"])
+        _tok(os, "<ConstComponentDim>"); _w_i32(os, c.get("const_component_dim", 0))
     elif t == "SoftmaxComponent":
         _tok(os, "<Dim>"); _w_i32(os, c["dim"])
         _tok(os, "<ValueSum>"); _w_vec(os, c.get("value_sum", np.zeros(0)), "<f8")
@@ -189,6 +206,10 @@ def _read_component(is_):
         _expect(is_, "<LinearParams>"); c["linear_params"] = _r_mat(is_)
         _expect(is_, "<BiasParams>"); c["bias_params"] = _r_vec(is_)
         _expect(is_, "<IsGradient>"); c["is_gradient"] = _r_bool(is_)
+    elif t == "SpliceComponent":
+        _expect(is_, "<InputDim>"); c["input_dim"] = _r_i32(is_)
+        _expect(is_, "<Context>"); c["context"] = _r_ivec(is_)
+        _expect(is_, "<ConstComponentDim>"); c["const_component_dim"] = _r_i32(is_)
     elif t == "SoftmaxComponent":
         _expect(is_, "<Dim>"); c["dim"] = _r_i32(is_)
         _expect(is_, "<ValueSum>"); c["value_sum"] = _r_vec(is_)
