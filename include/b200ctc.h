@@ -5,7 +5,9 @@
  *   - cudaStreamCreate/Destroy + cudaMalloc/cudaFree per minibatch (:209-217,
  *     247-248)  -> caller-owned workspace, any stream, optional no-sync
  *   - deriv->Scale(-1) in NnetCtcUpdater::Backprop (:323) -> grad_scale
- *   - deriv->Sum() NaN check (:232-234) -> *nonfinite flag written by the kernel
+ *   - deriv->Sum() NaN check (:232-234) and the costs.Sum()==costs.Sum() assert (:254) -> a flag word the
+ *     kernels set (bit 0: a non-finite cost, bit 1: a frame without a usable posterior), delivered through
+ *     b200ctcOptions.nonfinite_dev so that the caller can skip the update of a bad minibatch without a sync
  *   - FindRowMaxId for the accuracy (:270-273), a third read of the slab -> argmax_dev
  * Same data layout and semantics as include/ctc.h.
  */
@@ -29,6 +31,10 @@ typedef struct {
                          (what FindRowMaxId gives NnetCtcUpdater::ComputeTotAccuracy,
                          ctc-nnet-update.cc:270-273), produced by the pass that already
                          streams the row; rows past input_lengths get -1.  NULL: skipped. */
+  int *nonfinite_dev; /* optional DEVICE int: receives the call's flag word (0 = clean; bit 0 = a cost
+                         is inf/nan, bit 1 = some frame had no usable posterior).  Replaces the
+                         reference's blocking deriv->Sum() / costs.Sum() checks (:232-234, :254): a
+                         caller gates its weight update on it (b200rnnClipAndUpdateGuarded). */
 } b200ctcOptions;
 
 /* Same as get_workspace_size. */

@@ -110,6 +110,19 @@ b200rnnStatus_t b200rnnBackwardWeights(b200rnnPlan_t plan, int seq_length, const
 b200rnnStatus_t b200rnnClipAndUpdate(float *w, const float *dw, size_t n, float learning_rate,
                                      float clip, b200rnnStream_t stream);
 
+/*
+ * The same update as TrainNnetSimple applies it (src/ctc/ctc-nnet-train.cc:194-202, 220-245), in one pass:
+ *   delta == NULL (momentum 0: components update the model directly):  w += learning_rate * clamp(dw)
+ *   delta != NULL (the reference's gradient Nnet `delta_nnet`):        delta += learning_rate * clamp(dw);
+ *                                                                      w += delta;  delta *= momentum
+ * (`nnet->AddNnet(1.0, *delta_nnet); delta_nnet->Scale(momentum)`, :243-244).  0 <= momentum < 1 (:191).
+ * skip_flag_dev: optional DEVICE int; when it is non-zero at execution time the call changes nothing --
+ * the asynchronous form of the reference's "deriv sum is inf/nan" abort (ctc-nnet-update.cc:232-234);
+ * pass b200ctcOptions.nonfinite_dev of the minibatch's CTC call.
+ */
+b200rnnStatus_t b200rnnUpdate(float *w, float *delta, const float *dw, size_t n, float learning_rate,
+                              float clip, float momentum, const int *skip_flag_dev, b200rnnStream_t stream);
+
 /* ClipGradientComponent::Backprop, norm-based (:936-957): each row of d
  * [rows x cols] is scaled to L2-norm <= threshold, in place. */
 b200rnnStatus_t b200rnnClipRowNorm(float *d, int rows, int cols, float threshold,

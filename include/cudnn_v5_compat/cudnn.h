@@ -179,9 +179,10 @@ cudnnStatus_t cudnnRNNBackwardWeights(
     const void *reserveSpace, size_t reserveSpaceSizeInBytes);
 
 /* Selects the arithmetic of the kernels behind this API for descriptors created afterwards:
- * 0 = fp32 FMA (bit-for-bit reproducible, matches an fp32 reference to ~1e-6),
- * 1 = tensor cores (TF32 projections, BF16 recurrent operands, fp32 accumulate/state; default).
- * Also settable through the environment: B200_CUDNN_MATH=fp32|tensor.  Not part of cuDNN. */
+ * 0 = fp32 FMA (DEFAULT: what CUDNN_DATA_FLOAT asks for; matches an fp32 reference to ~1e-6),
+ * 1 = tensor cores (BF16 recurrent operands, TF32/BF16 projections, fp32 accumulate/state): ~10x
+ *     faster, outputs within the tolerance stated in DESIGN.md section 5.  Opt-in only.
+ * Also settable through the environment (read once): B200_CUDNN_MATH=tensor.  Not part of cuDNN. */
 void b200cudnnSetMath(int math);
 
 #ifdef __cplusplus

@@ -89,7 +89,6 @@ struct CtcDev {
   float *costs;           // [B]
   int *flags;             // [0]: non-finite cost seen
   int *argmax;            // optional [Tmax*B]: arg-max symbol per row (-1 on padded rows)
-  int dbg;                // tuning aid (B200CTC_DBG): ablation bits, wrong results
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -532,6 +531,7 @@ __global__ void __launch_bounds__(kK3Warps * 32) ctc_grad_kernel(CtcDev d, int s
   const float Z = warp_sum(z);
   const float zb = warp_sum(zblank);  // even states are blanks
   const float invZ = Z > 0.f ? 1.0f / Z : 0.f;
+  if (lane == 0 && !(Z > 0.f && Z < 3.0e38f)) atomicOr(d.flags, 2);   // no usable posterior for this frame
 
   // y = softmax(row), streamed
   if (vec) {
@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(kRingThreads, 2) ctc_grad_ring_kernel(CtcDev d
       mbar_wait(full_tab + (i % rc.NT), (uint32_t)(i / rc.NT) & 1u);
       float z = 0.f, zblank = 0.f;
       const float eb = e[0];
-      if (!(d.dbg & 2)) {
+      {
         // one (blank, label) pair per thread and iteration: states 2i and 2i+1
         for (int i2 = tid; i2 <= L; i2 += kRingConsumers) {
           const float2 a2 = *reinterpret_cast<const float2 *>(al + 2 * i2);
@@ -792,7 +792,7 @@ __global__ void __launch_bounds__(kRingThreads, 2) ctc_grad_ring_kernel(CtcDev d
       // ---- y = grad_scale * softmax(row), in place in the activation slot
       float4 *a4 = reinterpret_cast<float4 *>(act_base + (size_t)(i % rc.NA) * rc.act_bytes);
       mbar_wait(full_act + (i % rc.NA), (uint32_t)(i / rc.NA) & 1u);
-      const int n4 = (d.dbg & 16) ? 0 : (A >> 2);
+      const int n4 = A >> 2;
       for (int k0 = tid; k0 < n4; k0 += 4 * kRingConsumers) {
         float4 v[4];
 #pragma unroll
@@ -818,8 +818,9 @@ __global__ void __launch_bounds__(kRingThreads, 2) ctc_grad_ring_kernel(CtcDev d
         zb += part[8 + k];
       }
       const float invZ = Z > 0.f ? 1.0f / Z : 0.f;
+      if (tid == 0 && !(Z > 0.f && Z < 3.0e38f)) atomicOr(d.flags, 2);   // no usable posterior for this frame
       float *arow = reinterpret_cast<float *>(a4);
-      if (!(d.dbg & 1)) {
+      {
         for (int j = tid; j < nuniq; j += kRingConsumers) {
           const int q0 = s_us[j], q1 = s_us[j + 1];
           float acc = gam[s_pos[q0]];
@@ -917,7 +918,6 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int A,
 
 // pinned staging for the header block (one H2D copy per call) and the costs
 struct Staging {
-  std::mutex mu;
   unsigned char *pinned = nullptr;
   size_t cap = 0;
   float *costs = nullptr;
@@ -925,7 +925,51 @@ struct Staging {
   cudaEvent_t copied = nullptr;   // recorded after the last upload out of `pinned`
   bool pending = false;
 };
-Staging g_stage;
+
+// Tuning switches: read from the environment ONCE per process (none is needed in production).
+struct Tuning {
+  int force_p, ring, na, nt, profile, groups, one_stream;
+};
+const Tuning &tuning() {
+  static const Tuning t = [] {
+    auto geti = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
+    Tuning v;
+    v.force_p = geti("B200CTC_P", 0);
+    v.ring = geti("B200CTC_RING", -1);
+    v.na = geti("B200CTC_NA", 0);
+    v.nt = geti("B200CTC_NT", 0);
+    v.profile = geti("B200CTC_PROFILE", 0);
+    v.groups = geti("B200CTC_GROUPS", 0);
+    v.one_stream = geti("B200CTC_ONE_STREAM", 0);
+    return v;
+  }();
+  return t;
+}
+
+// Everything that belongs to ONE device: function attributes (cudaFuncSetAttribute is per device), the
+// side streams and events of the grouped launch, the SM count and the staging event.  Keyed by
+// cudaGetDevice() so that an in-process multi-GPU caller of the C ABI gets a consistent set per GPU.
+constexpr int kMaxGroups = 8;
+struct DeviceState {
+  int num_sms = 0;
+  bool k2_attr[3] = {false, false, false};   // P = 1, 2, 4
+  size_t smem3_set = 0, ring_set = 0;
+  cudaStream_t hp[kMaxGroups] = {};
+  cudaEvent_t e1[kMaxGroups] = {}, e2[kMaxGroups] = {};
+  Staging stage;
+};
+std::mutex g_mu;                       // one call at a time per process (the staging block is shared state)
+DeviceState *device_state() {          // call with g_mu held
+  static std::vector<DeviceState *> states;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return nullptr;
+  if ((size_t)dev >= states.size()) states.resize(dev + 1, nullptr);
+  if (!states[dev]) {
+    states[dev] = new DeviceState();
+    cudaDeviceGetAttribute(&states[dev]->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return states[dev];
+}
 
 bool ensure_pinned(Staging &s, size_t bytes, size_t ncosts) {
   if (bytes > s.cap) {
@@ -947,9 +991,9 @@ bool ensure_pinned(Staging &s, size_t bytes, size_t ncosts) {
 }
 
 template <int P>
-cudaError_t launch_k2(const CtcDev &dev, int B, int NT, int F, cudaStream_t stream) {
+cudaError_t launch_k2(const CtcDev &dev, int B, int NT, int F, cudaStream_t stream, DeviceState *ds) {
   const size_t smem = 2048 + sizeof(float) * 2 * kStages * kStageFloats;
-  static bool attr_done = false;
+  bool &attr_done = ds->k2_attr[P == 1 ? 0 : (P == 2 ? 1 : 2)];
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_kernel<P>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -974,7 +1018,11 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   if (workspace_bytes < p.total) return CTC_STATUS_INVALID_VALUE;
   cudaStream_t stream = (cudaStream_t)opt.stream;
 
-  std::lock_guard<std::mutex> lock(g_stage.mu);
+  std::lock_guard<std::mutex> lock(g_mu);
+  DeviceState *ds = device_state();
+  if (!ds) return CTC_STATUS_EXECUTION_FAILED;
+  Staging &g_stage = ds->stage;
+  const Tuning &tune = tuning();
   if (!ensure_pinned(g_stage, p.header_bytes, (size_t)B)) return CTC_STATUS_MEMOPS_FAILED;
   unsigned char *h = g_stage.pinned;
   UttMeta *hm = reinterpret_cast<UttMeta *>(h + p.off_meta);
@@ -1081,14 +1129,12 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   dev.costs = reinterpret_cast<float *>(w + p.off_costs);
   dev.flags = reinterpret_cast<int *>(w + p.off_flags);
   dev.argmax = opt.argmax_dev;
-  static const int dbg = getenv("B200CTC_DBG") ? atoi(getenv("B200CTC_DBG")) : 0;
-  dev.dbg = dbg;
 
   // K2 geometry: P pairs per thread so that one direction fits 512 threads
   const int npairs = p.maxL + 1;
   // (measured: above ~8 warps per direction the frame loop is issue-bound and 2 pairs per thread win)
   int P = npairs <= 256 ? 1 : (npairs <= 1024 ? 2 : 4);
-  static const int force_p = getenv("B200CTC_P") ? atoi(getenv("B200CTC_P")) : 0;   // tuning aid
+  const int force_p = tune.force_p;   // tuning aid
   if ((force_p == 2 || force_p == 4) && force_p > P) P = force_p;
   dev.P = P;
   // Launch K1 -> K2 -> K3 per utterance group.  With two groups on two streams the latency-bound
@@ -1098,7 +1144,7 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   const int smem_pitch = p.pitch_max;  // gammas of the label states of one row
   const size_t smem3 = sizeof(float) * (size_t)kK3Warps * smem_pitch;
   if (grad) {
-    static size_t smem3_set = 0;
+    size_t &smem3_set = ds->smem3_set;
     if (smem3 > smem3_set) {
       if (cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem3) != cudaSuccess)
@@ -1107,15 +1153,8 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
     }
   }
   // Wide alphabets: the persistent TMA-ring gradient kernel (see ctc_grad_ring_kernel)
-  static int num_sms = 0;
-  if (!num_sms) {
-    int devid = 0;
-    cudaGetDevice(&devid);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, devid);
-  }
-  const int env_ring = getenv("B200CTC_RING") ? atoi(getenv("B200CTC_RING")) : -1;   // tuning aids
-  static const int env_na = getenv("B200CTC_NA") ? atoi(getenv("B200CTC_NA")) : 0;
-  static const int env_nt = getenv("B200CTC_NT") ? atoi(getenv("B200CTC_NT")) : 0;
+  const int num_sms = ds->num_sms > 0 ? ds->num_sms : 148;
+  const int env_ring = tune.ring, env_na = tune.na, env_nt = tune.nt;   // tuning aids
   RingCfg rc;
   rc.NA = env_na >= 2 ? env_na : 4;
   rc.NT = env_nt >= 1 ? env_nt : 2;
@@ -1136,7 +1175,7 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   if (ring_bytes() > ((size_t)113 << 10) || rc.NA + rc.NT > 16) use_ring = false;
   const size_t ring_smem = ring_bytes();
   if (use_ring) {
-    static size_t ring_set = 0;
+    size_t &ring_set = ds->ring_set;
     if (ring_smem > ring_set) {
       if (cudaFuncSetAttribute(ctc_grad_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)ring_smem) != cudaSuccess)
@@ -1145,24 +1184,23 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
     }
   }
   // tuning aid: B200CTC_PROFILE=1 serialises the groups and prints the duration of each kernel
-  static const int prof_mode = getenv("B200CTC_PROFILE") ? atoi(getenv("B200CTC_PROFILE")) : 0;
+  const int prof_mode = tune.profile;
   const bool prof = prof_mode == 1;
   const bool timeline = prof_mode == 2;   // keeps the groups; prints each kernel's start/end on its own stream
   // (only worth it when the row kernels are long: a slab of >= 256 MB)
   const bool big = (size_t)p.Tmax * B * A >= ((size_t)64 << 20);
   // Utterance groups on separate streams: the latency-bound alpha/beta recursion of one group runs
   // under the bandwidth-bound row kernels of the others (only the first K2 and the last K3 stay exposed).
-  constexpr int kMaxGroups = 8;
-  const int env_groups = getenv("B200CTC_GROUPS") ? atoi(getenv("B200CTC_GROUPS")) : 0;
+  const int env_groups = tune.groups;
   int ngroups = B >= 16 ? 2 : 1;   // measured at B=256, A=4000: 1 -> 10.47 ms, 2 -> 9.95, 4 -> 9.91, 8 -> 9.99
   if (!big) ngroups = 1;
   if (env_groups >= 1 && env_groups <= kMaxGroups) ngroups = std::min(env_groups, B);
-  if (prof || getenv("B200CTC_ONE_STREAM")) ngroups = 1;
+  if (prof || tune.one_stream) ngroups = 1;
   // Several groups: the row kernels (K1, K3) of all groups run back to back on the caller's stream; each
   // group's alpha/beta kernel runs on its own HIGH-PRIORITY stream between them, so its CTAs are placed as
   // soon as the group's K1 is done instead of queueing behind the row kernels of the other groups.
-  static cudaStream_t hp[kMaxGroups] = {};
-  static cudaEvent_t e1[kMaxGroups] = {}, e2[kMaxGroups] = {};
+  cudaStream_t *hp = ds->hp;
+  cudaEvent_t *e1 = ds->e1, *e2 = ds->e2;
   if (ngroups > 1) {
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -1205,9 +1243,9 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
     set_group(gi);
     cudaStream_t st = ngroups > 1 ? hp[gi] : stream;
     if (ngroups > 1) cudaStreamWaitEvent(st, e1[gi], 0);
-    cudaError_t ce = P == 1   ? launch_k2<1>(dev, B, NT, F, st)
-                     : P == 2 ? launch_k2<2>(dev, B, NT, F, st)
-                              : launch_k2<4>(dev, B, NT, F, st);
+    cudaError_t ce = P == 1   ? launch_k2<1>(dev, B, NT, F, st, ds)
+                     : P == 2 ? launch_k2<2>(dev, B, NT, F, st, ds)
+                              : launch_k2<4>(dev, B, NT, F, st, ds);
     if (ce != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
     if (timeline) cudaEventRecord(tl[gi][2], st);
     if (ngroups > 1) cudaEventRecord(e2[gi], st);
@@ -1261,6 +1299,9 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   if (costs_dev &&
       cudaMemcpyAsync(costs_dev, dev.costs, sizeof(float) * B, cudaMemcpyDeviceToDevice, stream) !=
           cudaSuccess)
+    return CTC_STATUS_MEMOPS_FAILED;
+  if (opt.nonfinite_dev &&
+      cudaMemcpyAsync(opt.nonfinite_dev, dev.flags, sizeof(int), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
     return CTC_STATUS_MEMOPS_FAILED;
   if (!opt.no_sync) {
     if (cudaMemcpyAsync(g_stage.costs, dev.costs, sizeof(float) * B, cudaMemcpyDeviceToHost,
@@ -1332,6 +1373,7 @@ ctcStatus_t compute_ctc_loss(const float *const activations, float *gradients,
   o.stream = options.stream;
   o.no_sync = 0;
   o.argmax_dev = nullptr;
+  o.nonfinite_dev = nullptr;
   size_t need = 0;
   ctcStatus_t st = b200ctc_workspace_size(label_lengths, input_lengths, alphabet_size, minibatch, &need);
   if (st != CTC_STATUS_SUCCESS) return st;

@@ -229,13 +229,10 @@ ctcStatus_t b200ctc_format_input(const void *const *examples_host, const float *
   a.spk_dim = spk_dim;
   a.ignore_frames = p.ignore_frames;
   a.max_frames = p.max_frames;
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    if (cudaFuncSetAttribute(format_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-        cudaSuccess)
-      return CTC_STATUS_EXECUTION_FAILED;
-    smem_set = smem;
-  }
+  // (the attribute is per device: set it on every call that needs it -- a host-side table update, no sync)
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(format_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return CTC_STATUS_EXECUTION_FAILED;
   dim3 grid((p.max_frames + kTT - 1) / kTT, minibatch);
   format_input_kernel<<<grid, kThreads, smem, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? CTC_STATUS_SUCCESS : CTC_STATUS_EXECUTION_FAILED;

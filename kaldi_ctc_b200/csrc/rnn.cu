@@ -28,6 +28,9 @@ struct b200rnnPlan_st {
   // reserve layout (floats), per layer
   std::vector<size_t> r_gates[2], r_cell[2], r_y, r_bias;
   bool tc_bwd_used;  // the last BackwardData left fused bias gradients in the reserve
+  // tuning switches, read from the environment ONCE when the plan is created
+  bool force_stream, tc_no_bwd, phase_counters;
+  int force_bc;
   size_t reserve_floats;
   // workspace layout (floats)
   size_t w_colsum, w_splitk, w_pp[2], w_gates[2], w_stream, w_cell[2], workspace_floats;
@@ -47,16 +50,13 @@ int din_of(const b200rnnPlan_st *p, int layer) { return layer == 0 ? p->D : p->H
 b200rnnStatus_t ensure_geometry(b200rnnPlan_st *p) {
   if (p->geometry_ready) return B200RNN_STATUS_SUCCESS;
   p->NC = rec_fp32_pick_cluster(p->mode, p->H);  // 0: no on-chip configuration -> streaming kernels
-  if (getenv("B200RNN_FORCE_STREAM")) p->NC = 0;
+  if (p->force_stream) p->NC = 0;
   p->BC = 16;
   p->tcNC = p->tcBC = 0;
   if (p->math == 1 && rec_tc_supported(p->mode, p->H)) {
     p->tcNC = p->H / 32;
     p->tcBC = rec_tc_pick_chunk(p->H, p->B, p->dirs);
-    if (const char *e = getenv("B200RNN_TC_BC")) {  // tuning override: 4, 8 or 16
-      const int v = atoi(e);
-      if (v == 4 || v == 8 || v == 16) p->tcBC = v;
-    }
+    if (p->force_bc) p->tcBC = p->force_bc;  // tuning override: 4, 8 or 16
   }
   p->geometry_ready = true;
   return B200RNN_STATUS_SUCCESS;
@@ -68,6 +68,25 @@ __global__ void clip_update_kernel(float *w, const float *dw, size_t n, float lr
     float g = dw[i];
     if (clip > 0.f) g = fminf(fmaxf(g, -clip), clip);
     w[i] = fmaf(lr, g, w[i]);
+  }
+}
+
+// TrainNnetSimple's update through a gradient Nnet (ctc-nnet-train.cc:194-202, 243-244):
+//   delta += lr * clamp(dw);  w += delta;  delta *= momentum          (delta == NULL: w += lr * clamp(dw))
+// skipped altogether when *skip_flag != 0 (the CTC call's non-finite flag, include/b200ctc.h)
+__global__ void update_kernel(float *w, float *delta, const float *dw, size_t n, float lr, float clip, float momentum,
+                              const int *skip_flag) {
+  if (skip_flag && *skip_flag != 0) return;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float g = dw[i];
+    if (clip > 0.f) g = fminf(fmaxf(g, -clip), clip);
+    if (delta) {
+      const float d = fmaf(lr, g, delta[i]);
+      w[i] += d;
+      delta[i] = momentum * d;
+    } else {
+      w[i] = fmaf(lr, g, w[i]);
+    }
   }
 }
 
@@ -159,6 +178,18 @@ b200rnnStatus_t b200rnnCreatePlan(b200rnnPlan_t *plan, b200rnnMode_t mode, int b
   p->NC = p->BC = 0;
   p->launches = 0;
   p->profiling = false;
+  p->force_stream = getenv("B200RNN_FORCE_STREAM") != nullptr;
+  p->tc_no_bwd = getenv("B200RNN_TC_NO_BWD") != nullptr;
+#ifdef B200RNN_PHASE_COUNTERS
+  p->phase_counters = getenv("B200RNN_TC_PROFILE") != nullptr;
+#else
+  p->phase_counters = false;
+#endif
+  p->force_bc = 0;
+  if (const char *e = getenv("B200RNN_TC_BC")) {
+    const int v = atoi(e);
+    if (v == 4 || v == 8 || v == 16) p->force_bc = v;
+  }
   p->ev_used[0] = p->ev_used[1] = p->ev_used[2] = 0;
   // blob: all matrices of all pseudo-layers, then all biases
   const int npl = p->layers * p->dirs;
@@ -322,11 +353,10 @@ b200rnnStatus_t b200rnnForward(b200rnnPlan_t p, int T, const float *x, const flo
       if (p->tcNC) {
         a.NC = p->tcNC; a.U = 32; a.BC = p->tcBC;
         static long long *dbg = nullptr;
-        const bool prof = getenv("B200RNN_TC_PROFILE") != nullptr;
+        const bool prof = p->phase_counters;
         if (prof && !dbg) cudaMalloc(&dbg, 64 * sizeof(long long));
         if (prof) cudaMemsetAsync(dbg, 0, 64 * sizeof(long long), stream);
         a.dbg = prof ? dbg : nullptr;
-        a.dbg_flags = getenv("B200RNN_TC_DBG") ? atoi(getenv("B200RNN_TC_DBG")) : 0;
         CK(rec_tc_forward(a, stream));
         if (prof) {  // tuning aid: cycles per step of each phase (cluster 0, CTA 0)
           long long h[24];
@@ -387,11 +417,11 @@ b200rnnStatus_t b200rnnBackwardData(b200rnnPlan_t p, int T, const float *y, cons
     }
     {
       Timed tm(p, 1, stream);
-      if (p->tcNC && !getenv("B200RNN_TC_NO_BWD")) {
+      if (p->tcNC && !p->tc_no_bwd) {
         a.NC = p->tcNC; a.U = 32; a.BC = p->tcBC;
         a.bias_partial = rs + p->r_bias[l];
         static long long *dbgb = nullptr;
-        const bool profb = getenv("B200RNN_TC_PROFILE") != nullptr;
+        const bool profb = p->phase_counters;
         if (profb && !dbgb) cudaMalloc(&dbgb, 64 * sizeof(long long));
         if (profb) cudaMemsetAsync(dbgb, 0, 64 * sizeof(long long), stream);
         a.dbg = profb ? dbgb : nullptr;
@@ -513,6 +543,15 @@ b200rnnStatus_t b200rnnClipAndUpdate(float *w, const float *dw, size_t n, float 
   if (n == 0) return B200RNN_STATUS_SUCCESS;
   const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
   clip_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, dw, n, lr, clip);
+  return to_status(cudaGetLastError());
+}
+
+b200rnnStatus_t b200rnnUpdate(float *w, float *delta, const float *dw, size_t n, float lr, float clip,
+                              float momentum, const int *skip_flag_dev, b200rnnStream_t stream) {
+  if (!w || !dw || momentum < 0.f || momentum >= 1.f) return B200RNN_STATUS_INVALID_VALUE;
+  if (n == 0) return B200RNN_STATUS_SUCCESS;
+  const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
+  update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, delta, dw, n, lr, clip, momentum, skip_flag_dev);
   return to_status(cudaGetLastError());
 }
 

@@ -70,8 +70,8 @@ struct RecArgs {
   float *y;               // [T*B x H*dirs]
   const float *dy;        // bwd only
   int save;               // fwd: 1 = keep activations/cell for backward
-  long long *dbg;         // optional: per-phase cycle counters of cluster 0 / CTA 0 (tuning aid)
-  int dbg_flags;          // tuning experiments (B200RNN_TC_DBG): 1 = skip the HBM stores of the forward epilogue
+  long long *dbg;         // per-phase cycle counters of cluster 0 / CTA 0; only read by kernels built with
+                          // -DB200RNN_PHASE_COUNTERS (tuning builds), ignored by release kernels
   float *bias_partial;    // bwd (tensor kernels): [chunk][dir][side 0 = input, 1 = recurrent][G*H] sums of the
                           // gate gradients over time and the chunk's utterances (the bias gradients)
 };

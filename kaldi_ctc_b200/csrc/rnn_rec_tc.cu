@@ -69,6 +69,13 @@ constexpr int kThreads = 32 * kIssuers + 128;   // warps 0-3: MMA issuers (one a
 __host__ __device__ constexpr int threads_of(int EH) { return 32 * kIssuers + 128 * EH; }
 constexpr int kTmemCols = 256;  // D: columns [0,64) (four accumulators); A (R slice): columns [64, 64 + H/2)
 constexpr int kRingOffset = 48 * 1024;   // forward kernel: cp.async prefetch ring (32 KB) behind the h tiles + barriers
+// In-kernel phase counters (cycles per step of cluster 0 / CTA 0) are a build-time option
+// (-DB200RNN_PHASE_COUNTERS): release kernels carry no instrumentation in the per-step loops.
+#ifdef B200RNN_PHASE_COUNTERS
+constexpr bool kPhaseCounters = true;
+#else
+constexpr bool kPhaseCounters = false;
+#endif
 constexpr int kACol = 64;       // (several independent accumulators were measured: no gain, the
                                 //  burst is issue-bound at ~24 cycles per MMA, tools/mma_bench.cu)
 
@@ -217,7 +224,7 @@ rec_tc_fwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
     // warp-uniform copies (shuffle from lane 0) so the compiler keeps MMA operands in uniform registers
     const uint32_t hs0 = __shfl_sync(0xffffffffu, smem_u32(hs), 0);
     const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const bool prof = a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == 1;
+    const bool prof = kPhaseCounters && a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == 1;
     long long pm[4] = {0, 0, 0, 0};
     for (int step = 0; step < T; step++) {
       const int p = step & 1;
@@ -308,7 +315,7 @@ rec_tc_fwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
     float *bring = reinterpret_cast<float *>(smem + kRingOffset);
     uint64_t *pfbar = reinterpret_cast<uint64_t *>(smem + kRingOffset - 128);   // [kPF <= 16], kBulk only
     auto issue_bulk = [&](int step) {
-      if (step < T && !(a.dbg_flags & 2) && tid == 32 * kIssuers) {
+      if (step < T && tid == 32 * kIssuers) {
         const int t = dir ? T - 1 - step : step;
         uint64_t *bar = pfbar + step % kPF;
         mbar_expect_tx(bar, (uint32_t)kSlotFloats * 4u);
@@ -322,7 +329,7 @@ rec_tc_fwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
         issue_bulk(step);
         return;
       }
-      if (step < T && pload && !(a.dbg_flags & 2)) {
+      if (step < T && pload) {
         const int t = dir ? T - 1 - step : step;
         const float *pp = gates + ((size_t)t * B + b_lo) * GH + (size_t)pcol * H + unit;
         const uint32_t dst = smem_u32(pring + (size_t)(step % kPF) * 128 * BC);
@@ -360,19 +367,19 @@ rec_tc_fwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
     const uint32_t rhf_l = mapa_u32(smem_u32(hfull), lane < NC ? lane : 0);
     uint8_t *hstage = smem + kRingOffset + 32 * 1024;                          // kSW64: [2][16 rows][64 B]
 
-    const bool prof = a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == kIssuers;
+    const bool prof = kPhaseCounters && a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == kIssuers;
     long long pe[7] = {0, 0, 0, 0, 0, 0, 0};
-    const long long loop_t0 = a.dbg ? clock64() : 0;
+    const long long loop_t0 = (kPhaseCounters && a.dbg) ? clock64() : 0;
     for (int step = 0; step < T; step++) {
       const int t = dir ? T - 1 - step : step;
       const long long c0 = prof ? clock64() : 0;
       // this step's projection rows (copied kPF steps ago)
       float pre[BCL];
       if (kBulk) {
-        if (!(a.dbg_flags & 2)) mbar_wait(pfbar + step % kPF, (uint32_t)(step / kPF) & 1u);
+        mbar_wait(pfbar + step % kPF, (uint32_t)(step / kPF) & 1u);
         const float *ps = bring + (size_t)(step % kPF) * kSlotFloats + (eh * BCL * G + pcol) * 32 + ul;
 #pragma unroll
-        for (int b = 0; b < BCL; b++) pre[b] = (pload && !(a.dbg_flags & 2)) ? ps[b * G * 32] : 0.f;
+        for (int b = 0; b < BCL; b++) pre[b] = pload ? ps[b * G * 32] : 0.f;
       } else {
         asm volatile("cp.async.wait_group %0;" ::"n"(kPF - 1) : "memory");
         const float *ps = pring + (size_t)(step % kPF) * 128 * BC;
@@ -381,7 +388,7 @@ rec_tc_fwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
       }
       asm volatile("bar.sync 2, %0;" ::"n"(32 + 128 * EH) : "memory");
       const long long c1a = prof ? clock64() : 0;
-      if (!(a.dbg_flags & 4)) tc_fence_after();
+      tc_fence_after();
       const long long c1 = prof ? clock64() : 0;
       if (prof && lane == 0) a.dbg[16] += c1 - c1a;
       // only the BC columns of each issuer's accumulator that this chunk uses (TMEM reads are paced by bytes)
@@ -490,7 +497,7 @@ rec_tc_fwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
 #pragma unroll
       for (int j = 0; j < NJL; j++) {
         const int b = 4 * (jb + j) + s;
-        if (b < nb && !(a.dbg_flags & 1)) {
+        if (b < nb) {
           const size_t row = (size_t)t * B + b_lo + b;
           a.y[row * HO + dir * H + unit] = hnew[j];
           if (a.save) {
@@ -512,7 +519,7 @@ rec_tc_fwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
     }
     if (prof && lane == 0)
       for (int i = 0; i < 7; i++) a.dbg[i] = pe[i];
-    if (a.dbg && warp == kIssuers && lane == 0 && blockIdx.y < 16) a.dbg[32 + blockIdx.y + 16 * (crank != 0)] = clock64() - loop_t0;
+    if (kPhaseCounters && a.dbg && warp == kIssuers && lane == 0 && blockIdx.y < 16) a.dbg[32 + blockIdx.y + 16 * (crank != 0)] = clock64() - loop_t0;
   }
   tc_fence_before();
   __syncthreads();
@@ -619,7 +626,7 @@ rec_tc_bwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
     const uint32_t dg0 = __shfl_sync(0xffffffffu, smem_u32(dgs), 0);
     const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint64_t bd0 = smem_desc(dg0, 0, 1024, kLayoutSw128);
-    const bool profm = a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == 1;
+    const bool profm = kPhaseCounters && a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == 1;
     long long qm[3] = {0, 0, 0};
     for (int step = 0; step + 1 < T; step++) {
       const long long n0 = profm ? clock64() : 0;
@@ -651,7 +658,7 @@ rec_tc_bwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
     const int unit = crank * UT + ul;
     float *gates = a.gates[dir];
     float *cell = a.cell[dir];
-    const bool prof = a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == kIssuers;
+    const bool prof = kPhaseCounters && a.dbg != nullptr && crank == 0 && blockIdx.y == 0 && warp == kIssuers;
     long long pe[7] = {0, 0, 0, 0, 0, 0, 0};
     float carry[NJL];  // LSTM: dc carried to the previous step; GRU: dh * z
 #pragma unroll

@@ -23,7 +23,8 @@ class CtcOptions(ctypes.Structure):  # struct ctcOptions of include/ctc.h
 
 class B200CtcOptions(ctypes.Structure):  # b200ctcOptions of include/b200ctc.h
     _fields_ = [("blank_label", ctypes.c_int), ("grad_scale", ctypes.c_float),
-                ("stream", ctypes.c_void_p), ("no_sync", ctypes.c_int), ("argmax_dev", ctypes.c_void_p)]
+                ("stream", ctypes.c_void_p), ("no_sync", ctypes.c_int), ("argmax_dev", ctypes.c_void_p),
+                ("nonfinite_dev", ctypes.c_void_p)]
 
 
 class CtcError(RuntimeError):
@@ -126,14 +127,22 @@ class CtcLoss:
         return costs, (gradients if want_grad else None)
 
     def compute_extended(self, activations, flat_labels, label_lengths, input_lengths, blank=0,
-                         gradients=None, grad_scale=1.0, costs_dev=None, no_sync=False, argmax_dev=None):
+                         gradients=None, grad_scale=1.0, costs_dev=None, no_sync=False, argmax_dev=None,
+                         nonfinite_dev=None):
         torch = self.torch
+        assert activations.is_cuda and activations.dtype == torch.float32 and activations.is_contiguous()
         T, B, A = activations.shape
         fl, ll, il = _i32(flat_labels), _i32(label_lengths), _i32(input_lengths)
+        # the library derives T from input_lengths and writes gradient rows for t < max(input_lengths) only:
+        # a longer slab would leave stale rows (the reference zero-fills deriv first, ctc-nnet-update.cc:222)
+        assert len(ll) == B and len(il) == B and int(il.max()) == T
+        assert gradients is None or (gradients.dtype == torch.float32 and gradients.is_contiguous()
+                                     and tuple(gradients.shape) == (T, B, A))
         ws = self._workspace(workspace_size(ll, il, A))
         costs = None if no_sync else np.zeros(B, dtype=np.float32)
         opt = B200CtcOptions(blank, grad_scale, torch.cuda.current_stream(self.device).cuda_stream,
-                             1 if no_sync else 0, argmax_dev.data_ptr() if argmax_dev is not None else None)
+                             1 if no_sync else 0, argmax_dev.data_ptr() if argmax_dev is not None else None,
+                             nonfinite_dev.data_ptr() if nonfinite_dev is not None else None)
         with torch.cuda.device(self.device):
             st = lib().b200ctc_loss(activations.data_ptr(),
                                     gradients.data_ptr() if gradients is not None else None,

@@ -44,27 +44,33 @@ class AffineComponent:
         return out
 
     def Backprop(self, in_value, out_deriv, to_update=None, in_deriv=None, grad_out=None):
+        """UpdateSimple (bias += lr * colsum(dY), W += lr * dY^T X) goes through raw gradient buffers and
+        Update(), so that it can be gated on the CTC call's non-finite flag, routed through the momentum
+        buffers, or summed over ranks first (grad_out given: only the raw gradients are produced)."""
         t = self.torch
         rows, K, N = in_value.shape[0], self.InputDim(), self.OutputDim()
         if in_deriv is None:
             in_deriv = t.empty(rows, K, device=self.device)
         rnn.gemm(t, 0, 0, rows, K, N, 1.0, out_deriv, N, self.linear_params_, K, 0.0, in_deriv, K, math=self.math)
-        if to_update is not None and grad_out is None:
-            # UpdateSimple: bias += lr * colsum, W += lr * dY^T X
-            rnn.column_sums_scaled(t, out_deriv, to_update.bias_params_, to_update.learning_rate_, self.ws)
-            rnn.gemm(t, 1, 0, N, K, rows, to_update.learning_rate_, out_deriv, N, in_value, K, 1.0,
-                     to_update.linear_params_, K, math=self.math, workspace=self.ws)
-        elif grad_out is not None:  # data-parallel: raw gradients, applied after the all-reduce
+        if to_update is not None or grad_out is not None:
+            if grad_out is None:
+                if getattr(self, "gW_", None) is None:
+                    self.gW_, self.gb_ = t.empty_like(self.linear_params_), t.empty_like(self.bias_params_)
+                grad_out = (self.gW_, self.gb_)
             gW, gb = grad_out
             rnn.column_sums(t, out_deriv, gb, False, self.ws)
             rnn.gemm(t, 1, 0, N, K, rows, 1.0, out_deriv, N, in_value, K, 0.0, gW, K, math=self.math,
                      workspace=self.ws)
+            if to_update is not None:
+                to_update.Update(gW, gb)
         return in_deriv
 
     def Update(self, gW, gb):
         t = self.torch
-        rnn.clip_and_update(t, self.linear_params_, gW, self.learning_rate_, 0.0)
-        rnn.clip_and_update(t, self.bias_params_, gb, self.learning_rate_, 0.0)
+        dW, db = getattr(self, "delta_", None) or (None, None)
+        mom, flag = getattr(self, "momentum_", 0.0), getattr(self, "skip_flag_", None)
+        rnn.update(t, self.linear_params_, gW, self.learning_rate_, 0.0, delta=dW, momentum=mom, skip_flag=flag)
+        rnn.update(t, self.bias_params_, gb, self.learning_rate_, 0.0, delta=db, momentum=mom, skip_flag=flag)
 
 
 class ClipGradientComponent:
@@ -131,7 +137,7 @@ class NnetCtcUpdater:
     """Mirror of kaldi::ctc::NnetCtcUpdater for the BLSTM/BiGRU + CTC topology."""
 
     def __init__(self, spec, blobs, affine_w, affine_b, minibatch, max_frames, device="cuda:0",
-                 math=rnn.MATH_FP32, world=1, overlap_weights=True):
+                 math=rnn.MATH_FP32, world=1, overlap_weights=True, momentum=0.0):
         self.torch = t = _lib.require_cuda()
         self.device = t.device(device)
         self.spec, self.B, self.math, self.world = spec, minibatch, math, world
@@ -157,6 +163,20 @@ class NnetCtcUpdater:
         self.logits = t.empty(rows, spec.A, device=self.device)
         self.deriv = t.empty(rows, spec.A, device=self.device)
         self.dact = [t.empty(rows, spec.H * dirs, device=self.device) for _ in range(2)]
+        # the CTC call's flag word (non-finite cost / no usable posterior): every weight update of the step is
+        # gated on it on the device, the asynchronous form of the reference's aborts (ctc-nnet-update.cc:232-234,254)
+        self.nonfinite_dev = t.zeros(1, dtype=t.int32, device=self.device)
+        self.nonfinite_host = t.zeros(1, dtype=t.int32).pin_memory()
+        # momentum: the reference trains through a zeroed copy of the model, `delta_nnet`
+        # (ctc-nnet-train.cc:194-202): delta += lr*grad; nnet += delta; delta *= momentum (:243-244)
+        assert 0.0 <= momentum < 1.0
+        self.momentum = momentum
+        for c in self.rnns:
+            c.skip_flag_, c.momentum_ = self.nonfinite_dev, momentum
+            c.delta_ = t.zeros_like(c.filter_params_) if momentum != 0.0 else None
+        a = self.affine
+        a.skip_flag_, a.momentum_ = self.nonfinite_dev, momentum
+        a.delta_ = (t.zeros_like(a.linear_params_), t.zeros_like(a.bias_params_)) if momentum != 0.0 else None
         self.costs_dev = t.zeros(minibatch, device=self.device)
         self.costs_host = t.zeros(minibatch, dtype=t.float32).pin_memory()
         self.best_pdf = None       # [rows] int32, filled by the CTC pass when accuracy is wanted
@@ -229,13 +249,14 @@ class NnetCtcUpdater:
         # output.FindRowMaxId of ComputeTotAccuracy (:270-273) into the pass that reads the rows anyway
         self.ctc.compute_extended(act, flat_labels, label_lengths, input_lengths, blank=0, gradients=grad,
                                   grad_scale=-1.0, costs_dev=self.costs_dev, no_sync=True,
-                                  argmax_dev=self.best_pdf if want_best_pdf else None)
+                                  argmax_dev=self.best_pdf if want_best_pdf else None,
+                                  nonfinite_dev=self.nonfinite_dev)
         self.costs_host.copy_(self.costs_dev, non_blocking=True)
+        self.nonfinite_host.copy_(self.nonfinite_dev, non_blocking=True)
         if want_best_pdf:
             self.best_pdf_host[:rows].copy_(self.best_pdf[:rows], non_blocking=True)
         if sync:
-            self.torch.cuda.current_stream(self.device).synchronize()
-            return float(self.costs_host.sum())
+            return self.last_objf()
         return None
 
     def Backprop(self, T, update=True):
@@ -255,6 +276,7 @@ class NnetCtcUpdater:
         if dp:
             from .parallel import GradientReducer
             red = GradientReducer()
+            red.submit_max(self.nonfinite_dev)   # a bad minibatch on ANY rank skips the update on EVERY rank
             d = self.affine.Backprop(top_in, self.deriv[:rows], None, in_deriv=self.dact[0][:rows],
                                      grad_out=(self.gW, self.gb))
             red.submit([self.gW, self.gb], lambda: self.affine.Update(self.gW, self.gb))
@@ -302,7 +324,16 @@ class NnetCtcUpdater:
             else:
                 red.finish()
         if side is not None:
-            t.cuda.current_stream(self.device).wait_stream(side)
+            cur = t.cuda.current_stream(self.device)
+            ev = getattr(self, "tail_events", None)
+            if ev is not None:   # measurement aid: how long the step waits for the side stream (weight GEMMs of the
+                #                  bottom layer, all-reduce, updates) after the main stream has run dry
+                e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+                e0.record(cur)
+            cur.wait_stream(side)
+            if ev is not None:
+                e1.record(cur)
+                ev.append((e0, e1))
         return d
 
     def ComputeTotAccuracy(self, T, flat_labels, label_lengths, input_lengths):
@@ -335,7 +366,14 @@ class NnetCtcUpdater:
         return self.last_objf()
 
     def last_objf(self):
+        """tot_objf of the last minibatch.  Raises where the reference aborts ("Error in this batch, deriv sum
+        is inf/nan", ctc-nnet-update.cc:232-234; costs.Sum() != costs.Sum(), :254); the weight updates of such a
+        minibatch were skipped on the device."""
         self.torch.cuda.current_stream(self.device).synchronize()
+        flag = int(self.nonfinite_host[0])
+        if flag:
+            raise ctc.CtcError("Error in this batch: non-finite CTC cost or posterior (flag %d); "
+                               "the weight update of this minibatch was skipped" % flag)
         return float(self.costs_host.sum())
 
     def launches_per_step(self):
@@ -346,4 +384,4 @@ class NnetCtcUpdater:
         for c in self.rnns:
             n += c.launch_counts.get("fwd", 0) + c.launch_counts.get("bwd_data", 0) + \
                 c.launch_counts.get("bwd_weights", 0) + 1 + 1  # + ClipAndUpdate + ClipRowNorm
-        return n + 3 + 4 + 2
+        return n + 3 + 4 + 2 + 2   # CTC 3, affine GEMMs 3 (+ split-K reduce), column sums 2, affine updates 2

@@ -29,6 +29,11 @@ class GradientReducer:
         works = [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True) for t in tensors]
         self.pending.append((works, on_done))
 
+    def submit_max(self, flag):
+        """all-reduce(max) of a small flag tensor, ahead of the gradients on the same communicator."""
+        self.pending.append(([dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group, async_op=True)],
+                             lambda: None))
+
     def finish(self):
         for works, on_done in self.pending:
             for w in works:

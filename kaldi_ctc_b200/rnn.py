@@ -40,6 +40,7 @@ def lib():
         L.b200rnnBackwardData.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp]
         L.b200rnnBackwardWeights.argtypes = [vp, i, vp, vp, vp, vp, vp, vp]
         L.b200rnnClipAndUpdate.argtypes = [vp, vp, sz, f, f, vp]
+        L.b200rnnUpdate.argtypes = [vp, vp, vp, sz, f, f, f, vp, vp]
         L.b200rnnClipRowNorm.argtypes = [vp, i, i, f, vp]
         L.b200rnnGemm.argtypes = [i, i, i, i, i, f, vp, i, vp, i, f, vp, i, vp, i, vp, sz, vp]
         L.b200rnnColumnSums.argtypes = [vp, i, i, i, f, vp, i, vp, sz, vp]
@@ -266,11 +267,14 @@ class CuDNNRecurrentComponent:
         to_update.Update(self.filter_params_grad_, self.clip_gradient_)
 
     def Update(self, filter_params_grad, clip):
+        """filter_params_ += learning_rate_ * clamp(grad) (:602-603, 612-614).  With `delta_` set (the
+        reference's gradient Nnet of TrainNnetSimple, ctc-nnet-train.cc:194-202) the step goes through it with
+        `momentum_`; `skip_flag_` (device int, the CTC call's non-finite flag) turns the update into a no-op."""
         torch = self.torch
         with torch.cuda.device(self.device):
-            _check(lib().b200rnnClipAndUpdate(self.filter_params_.data_ptr(), filter_params_grad.data_ptr(),
-                                              filter_params_grad.numel(), self.learning_rate_, clip,
-                                              _stream(torch, self.device)), "b200rnnClipAndUpdate")
+            update(torch, self.filter_params_, filter_params_grad, self.learning_rate_, clip,
+                   delta=getattr(self, "delta_", None), momentum=getattr(self, "momentum_", 0.0),
+                   skip_flag=getattr(self, "skip_flag_", None))
 
     # the remaining UpdatableComponent surface acts on the flat blob (:723-772)
     def NumParameters(self):
@@ -320,6 +324,14 @@ def column_sums_scaled(torch, a, out, alpha, workspace):
 def clip_and_update(torch, w, dw, lr, clip):
     _check(lib().b200rnnClipAndUpdate(w.data_ptr(), dw.data_ptr(), w.numel(), lr, clip,
                                       _stream(torch, w.device)), "b200rnnClipAndUpdate")
+
+
+def update(torch, w, dw, lr, clip, delta=None, momentum=0.0, skip_flag=None):
+    """b200rnnUpdate: delta None -> w += lr*clamp(dw); else delta += lr*clamp(dw); w += delta; delta *= momentum."""
+    _check(lib().b200rnnUpdate(w.data_ptr(), delta.data_ptr() if delta is not None else None, dw.data_ptr(),
+                               w.numel(), lr, clip, momentum,
+                               skip_flag.data_ptr() if skip_flag is not None else None,
+                               _stream(torch, w.device)), "b200rnnUpdate")
 
 
 def clip_row_norm(torch, d, threshold):
