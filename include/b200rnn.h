@@ -85,6 +85,20 @@ b200rnnStatus_t b200rnnForward(b200rnnPlan_t plan, int seq_length, const float *
                                float *y, void *workspace, void *reserve, b200rnnStream_t stream);
 
 /*
+ * b200rnnForward with the BF16 side channel of the tensor mode.  In B200RNN_MATH_TENSOR the persistent recurrent
+ * kernel can leave a BF16 copy of y (it packs h_t to BF16 for its own recurrence anyway), and the hoisted input
+ * projection of the NEXT component then runs kind::f16 from half the operand bytes instead of TF32 from fp32.
+ *   x_bf16  optional DEVICE [T*B x D] BF16 copy of x (the producing component's y_bf16); NULL: the library converts
+ *           x itself when that pays (D >= 128), into the workspace
+ *   y_bf16  optional DEVICE [T*B x H*dirs] BF16, receives the copy of y; NULL: not produced
+ * Both are ignored in B200RNN_MATH_FP32 and for shapes that run the fp32 / streaming recurrent kernels.  The fp32
+ * x and y stay the interface of record (the reference's CuMatrix buffers); the copies only feed GEMM operands.
+ */
+b200rnnStatus_t b200rnnForwardEx(b200rnnPlan_t plan, int seq_length, const float *x, const void *x_bf16,
+                                 const float *w, float *y, void *y_bf16, void *workspace, void *reserve,
+                                 b200rnnStream_t stream);
+
+/*
  * cudnnRNNBackwardData (RecurrentBackwardData, :577-587) with dhy = dcy = 0:
  * dx [T*B x D] from dy, using the reserve of the matching forward call.
  * Leaves the gate gradients in the reserve for b200rnnBackwardWeights.
@@ -127,6 +141,27 @@ b200rnnStatus_t b200rnnUpdate(float *w, float *delta, const float *dw, size_t n,
  * [rows x cols] is scaled to L2-norm <= threshold, in place. */
 b200rnnStatus_t b200rnnClipRowNorm(float *d, int rows, int cols, float threshold,
                                    b200rnnStream_t stream);
+
+/*
+ * The whole of ClipGradientComponent::Backprop (nnet-cudnn-component.cc:912-1055), stream-ordered and without a
+ * host round trip: norm-based row clipping of `deriv` [rows x cols] in place (:936-957), the component's counters,
+ * and the stochastic self-repair term RepairGradients (:970-1055).
+ *   in_value             the component's forward input [rows x cols] (what the self-repair pushes towards
+ *                        self_repair_target); NULL disables self-repair
+ *   attempt_repair       the caller's coin: RandUniform() <= repair_probability (0.5, :979-984), drawn on the host
+ *   counters_dev         DEVICE int[4] = {num_clipped_, count_, num_self_repaired_, num_backpropped_} of the
+ *                        component being updated (to_update), incremented as the reference does; may be NULL
+ *   decide_counters_dev  DEVICE int[4] the repair decision reads (`this` in the reference: count_ > 0 and
+ *                        num_clipped_/count_ > threshold, :983-995); pass counters_dev when the net updates itself
+ *                        (with momentum the reference updates a copy, so `this` stays at its start-up values)
+ *   workspace            DEVICE, b200rnnClipGradientWorkspaceSize(rows) bytes
+ */
+b200rnnStatus_t b200rnnClipGradientWorkspaceSize(int rows, size_t *bytes);
+b200rnnStatus_t b200rnnClipGradientBackprop(float *deriv, const float *in_value, int rows, int cols,
+                                            float clipping_threshold, float self_repair_clipped_proportion_threshold,
+                                            float self_repair_target, float self_repair_scale, int attempt_repair,
+                                            int *counters_dev, const int *decide_counters_dev, void *workspace,
+                                            size_t workspace_bytes, b200rnnStream_t stream);
 
 /* Plain row-major fp32 GEMM used for the adjacent AffineComponent
  * (src/nnet2/nnet-component.cc:1184-1226): C[M x N] = alpha*op(A)*op(B) + beta*C

@@ -160,6 +160,10 @@ class NnetCtcUpdater:
         # forward_data_ of the reference: one buffer per component boundary, reused every minibatch
         self.x_dev = t.empty(rows, spec.D, device=self.device)
         self.acts = [t.empty(rows, spec.H * dirs, device=self.device) for _ in blobs]
+        # tensor mode: BF16 copies of the layer outputs, written by the recurrent kernels, read by the next layer's
+        # projection GEMM (b200rnnForwardEx); the fp32 buffers above stay the interface of record
+        self.acts16 = [t.empty(rows, spec.H * dirs, device=self.device, dtype=t.bfloat16) if math == rnn.MATH_TENSOR and
+                       l + 1 < len(blobs) else None for l in range(len(blobs))]
         self.logits = t.empty(rows, spec.A, device=self.device)
         self.deriv = t.empty(rows, spec.A, device=self.device)
         self.dact = [t.empty(rows, spec.H * dirs, device=self.device) for _ in range(2)]
@@ -232,9 +236,11 @@ class NnetCtcUpdater:
 
     def Propagate(self, T):
         rows = T * self.B
-        h = self.x_dev[:rows]
-        for c, clip, out in zip(self.rnns, self.clips, self.acts):
-            h = clip.Propagate(c.Propagate(h, out[:rows]))
+        h, h16 = self.x_dev[:rows], None
+        for c, clip, out, out16 in zip(self.rnns, self.clips, self.acts, self.acts16):
+            o16 = out16[:rows] if out16 is not None else None
+            h = clip.Propagate(c.Propagate(h, out[:rows], inp16=h16, out16=o16))   # (ClipGradient forward = identity)
+            h16 = o16
         return self.affine.Propagate(h, self.logits[:rows])
 
     def ComputeObjfAndDeriv(self, T, flat_labels, label_lengths, input_lengths, sync=True, want_best_pdf=False):

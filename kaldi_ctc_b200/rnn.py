@@ -37,6 +37,7 @@ def lib():
         L.b200rnnGetWorkspaceSize.argtypes = [vp, ctypes.POINTER(sz)]
         L.b200rnnGetReserveSize.argtypes = [vp, ctypes.POINTER(sz)]
         L.b200rnnForward.argtypes = [vp, i, vp, vp, vp, vp, vp, vp]
+        L.b200rnnForwardEx.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp, vp]
         L.b200rnnBackwardData.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp]
         L.b200rnnBackwardWeights.argtypes = [vp, i, vp, vp, vp, vp, vp, vp]
         L.b200rnnClipAndUpdate.argtypes = [vp, vp, sz, f, f, vp]
@@ -195,7 +196,9 @@ class CuDNNRecurrentComponent:
     def SetParams(self, blob):
         self.filter_params_ = self.torch.as_tensor(np.asarray(blob, dtype=np.float32)).to(self.device).clone()
 
-    def Propagate(self, inp, out=None, inference=False):
+    def Propagate(self, inp, out=None, inference=False, inp16=None, out16=None):
+        """inp16 / out16 (tensor mode only): optional BF16 copies of inp (from the producing component) and of the
+        output (for the next one), [rows, dim] torch.bfloat16 -- b200rnnForwardEx's side channel."""
         torch = self.torch
         if self.mini_batch_ == 0:
             self.InitMiniBatch(1)
@@ -209,9 +212,16 @@ class CuDNNRecurrentComponent:
         # :534: B==1 -> cudnnRNNForwardInference (no reserve space)
         reserve = None if (self.mini_batch_ == 1 or inference) else self.reserve_space_.data_ptr()
         with torch.cuda.device(self.device):
-            _check(lib().b200rnnForward(self.plan.h, T, inp.data_ptr(), self.filter_params_.data_ptr(),
-                                        out.data_ptr(), self.work_space_.data_ptr(), reserve,
-                                        _stream(torch, self.device)), "b200rnnForward")
+            if inp16 is not None:
+                assert inp16.dtype == torch.bfloat16 and inp16.is_contiguous() and tuple(inp16.shape) == tuple(inp.shape)
+            if out16 is not None:
+                assert out16.dtype == torch.bfloat16 and out16.is_contiguous() and tuple(out16.shape) == tuple(out.shape)
+            _check(lib().b200rnnForwardEx(self.plan.h, T, inp.data_ptr(),
+                                          inp16.data_ptr() if inp16 is not None else None,
+                                          self.filter_params_.data_ptr(), out.data_ptr(),
+                                          out16.data_ptr() if out16 is not None else None,
+                                          self.work_space_.data_ptr(), reserve,
+                                          _stream(torch, self.device)), "b200rnnForwardEx")
         self.launch_counts["fwd"] = self.plan.last_launches()
         return out
 

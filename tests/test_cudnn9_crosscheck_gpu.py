@@ -19,7 +19,8 @@ def test_against_cudnn9(mode, bidir, layers):
     comp.InitFromString("learning-rate=0.0 num-layers=%d input-dim=%d output-dim=%d rnn-mode=%d bidirectional=%s "
                         "max-seq-length=32 clip-gradient=0 mini-batch=%d" % (layers, D, H, mode, "true" if bidir else "false", B))
     rng = np.random.default_rng(3)
-    w = (rng.standard_normal(comp.NumParameters()) * 0.2).astype(np.float32)
+    # (plain tanh / relu recurrences amplify round-off when the recurrent matrix is expansive: keep them contractive)
+    w = (rng.standard_normal(comp.NumParameters()) * (0.2 if mode >= 2 else 0.08)).astype(np.float32)
     comp.SetParams(w)
     x = rng.standard_normal((T * B, D)).astype(np.float32)
     dy = rng.standard_normal((T * B, H * dirs)).astype(np.float32)
