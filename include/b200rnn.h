@@ -85,20 +85,6 @@ b200rnnStatus_t b200rnnForward(b200rnnPlan_t plan, int seq_length, const float *
                                float *y, void *workspace, void *reserve, b200rnnStream_t stream);
 
 /*
- * b200rnnForward with the BF16 side channel of the tensor mode.  In B200RNN_MATH_TENSOR the persistent recurrent
- * kernel can leave a BF16 copy of y (it packs h_t to BF16 for its own recurrence anyway), and the hoisted input
- * projection of the NEXT component then runs kind::f16 from half the operand bytes instead of TF32 from fp32.
- *   x_bf16  optional DEVICE [T*B x D] BF16 copy of x (the producing component's y_bf16); NULL: the library converts
- *           x itself when that pays (D >= 128), into the workspace
- *   y_bf16  optional DEVICE [T*B x H*dirs] BF16, receives the copy of y; NULL: not produced
- * Both are ignored in B200RNN_MATH_FP32 and for shapes that run the fp32 / streaming recurrent kernels.  The fp32
- * x and y stay the interface of record (the reference's CuMatrix buffers); the copies only feed GEMM operands.
- */
-b200rnnStatus_t b200rnnForwardEx(b200rnnPlan_t plan, int seq_length, const float *x, const void *x_bf16,
-                                 const float *w, float *y, void *y_bf16, void *workspace, void *reserve,
-                                 b200rnnStream_t stream);
-
-/*
  * cudnnRNNBackwardData (RecurrentBackwardData, :577-587) with dhy = dcy = 0:
  * dx [T*B x D] from dy, using the reserve of the matching forward call.
  * Leaves the gate gradients in the reserve for b200rnnBackwardWeights.
@@ -190,7 +176,9 @@ double b200rnnForwardFlops(b200rnnPlan_t plan, int seq_length);
 
 /* Optional CUDA-event timing of the kernels a plan launches (the reference times
  * every cuDNN call into CuDevice::AccuProfile, src/cudamatrix/cudnn-recurrent.cc:25-30).
- * Categories: 0 = recurrent forward kernel, 1 = recurrent backward kernel, 2 = GEMMs.
+ * Categories: 0 = recurrent forward kernel, 1 = recurrent backward kernel, 2 = projection / dx GEMMs (Forward,
+ * BackwardData), 3 = weight-gradient GEMMs (BackwardWeights; callers run them on a side stream, where their
+ * elapsed times overlap other kernels).
  * GetProfile synchronises the recorded events, returns the sums since the previous
  * GetProfile of that category and resets them. */
 b200rnnStatus_t b200rnnSetProfiling(b200rnnPlan_t plan, int enable);

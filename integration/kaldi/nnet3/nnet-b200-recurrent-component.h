@@ -47,7 +47,7 @@ class B200RecurrentPrecomputedIndexes: public ComponentPrecomputedIndexes {
 class B200RecurrentComponent: public UpdatableComponent {
  public:
   B200RecurrentComponent(): input_dim_(0), hidden_dim_(0), num_layers_(1), rnn_mode_(B200RNN_LSTM),
-      bidirectional_(true), max_seq_length_(2000), clip_gradient_(5.0), math_(B200RNN_MATH_TENSOR) { }
+      bidirectional_(true), max_seq_length_(2000), clip_gradient_(5.0), math_(B200RNN_MATH_FP32) { }
   B200RecurrentComponent(const B200RecurrentComponent &o):
       UpdatableComponent(o), input_dim_(o.input_dim_), hidden_dim_(o.hidden_dim_), num_layers_(o.num_layers_),
       rnn_mode_(o.rnn_mode_), bidirectional_(o.bidirectional_), max_seq_length_(o.max_seq_length_),
@@ -74,8 +74,11 @@ class B200RecurrentComponent: public UpdatableComponent {
     cfl->GetValue("clip-gradient", &clip_gradient_);
     cfl->GetValue("param-stddev", &param_stddev);
     cfl->GetValue("bias-stddev", &bias_stddev);
-    int32 exact = 0;
-    if (cfl->GetValue("exact-fp32", &exact) && exact) math_ = B200RNN_MATH_FP32;
+    // exact fp32 kernels by default (what an fp32 nnet3 model expects); exact-fp32=0 opts into the tensor-core mode
+    // (BF16 recurrent operands, TF32 projections; tolerance in DESIGN.md section 5)
+    int32 exact = 1;
+    cfl->GetValue("exact-fp32", &exact);
+    math_ = exact ? B200RNN_MATH_FP32 : B200RNN_MATH_TENSOR;
     if (!ok || cfl->HasUnusedValues() || rnn_mode_ < 0 || rnn_mode_ > 3)
       KALDI_ERR << "Bad initializer " << cfl->WholeLine();
     b200rnnPlan_t plan = GetPlan(1);

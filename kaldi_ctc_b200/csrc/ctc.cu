@@ -89,28 +89,7 @@ struct CtcDev {
   float *costs;           // [B]
   int *flags;             // [0]: non-finite cost seen
   int *argmax;            // optional [Tmax*B]: arg-max symbol per row (-1 on padded rows)
-  long long *pc;          // phase counters (tuning builds with -DB200CTC_PHASE_COUNTERS only; NULL otherwise)
 };
-
-// In-kernel phase counters of the streaming kernels are a BUILD-time option: release kernels carry none.
-#ifdef B200CTC_PHASE_COUNTERS
-#define PC_DECL long long pc_t0 = clock64(), pc_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
-#define PC_MARK(i)                    \
-  do {                                \
-    const long long pc_t1 = clock64(); \
-    pc_acc[i] += pc_t1 - pc_t0;       \
-    pc_t0 = pc_t1;                    \
-  } while (0)
-#define PC_FLUSH(cond, base)                                             \
-  do {                                                                   \
-    if (d.pc && (cond))                                                  \
-      for (int pc_i = 0; pc_i < 8; pc_i++) atomicAdd((unsigned long long *)d.pc + (base) + pc_i, (unsigned long long)pc_acc[pc_i]); \
-  } while (0)
-#else
-#define PC_DECL
-#define PC_MARK(i)
-#define PC_FLUSH(cond, base)
-#endif
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -871,640 +850,12 @@ __global__ void __launch_bounds__(kRingThreads, 2) ctc_grad_ring_kernel(CtcDev d
 }
 
 // ===========================================================================
-// Streaming path (wide alphabets, many utterances): ONE persistent CTA per utterance, two kernels
-// ===========================================================================
-// The three-kernel path above reads the slab twice, writes it once and moves alpha, beta and E through HBM
-// (38 GB for 21.6 GB algorithmic on the A = 4000, B = 256 stress case), with the alpha/beta recursion as a
-// separate, latency-bound phase.  Here the recursions RIDE the two slab reads, warp-specialised so that the
-// per-frame dependent chain is only the recursion itself:
-//   SA ctc_stream_alpha   forward in time.  Producer thread: ring of TMA bulk copies of the utterance's rows.
-//        4 "stats" warps take whole rows round-robin (log-sum-exp + arg-max out of shared memory, several frames
-//        ahead).  4 "chain" warps gather their states' emissions from the row in shared memory and advance alpha
-//        (same per-thread integer offsets and re-centring as K2), one named barrier per frame among themselves.
-//        Written to HBM: alpha_t (8 B per state pair) with the row's log-sum-exp in the unused last slot.
-//   SB ctc_stream_beta_grad   backward in time.  Row ring + a ring of alpha rows.  4 chain warps: gather, beta
-//        step, gamma = alpha * beta / (y p) straight from registers into a small ring in shared memory.  4 "row"
-//        warps, a few frames behind: grad_scale * softmax IN PLACE in the row slot, per-label masses through the
-//        CSR subtracted in place, then ONE TMA bulk store of the row.  beta and E never exist in HBM.  Padded rows
-//        are zero-filled by the CTA when its utterance is done, which keeps the memory system busy while the longest
-//        utterances finish.
-// HBM traffic: 2 reads + 1 write of the slab + alpha written and read once (8 B per pair and frame).
-constexpr int kSChain = 128;         // chain threads (warps 0-3)
-constexpr int kSC = 256;             // consumer threads (chain + stats / row warps)
-constexpr int kSThreads = kSC + 32;  // + the producer warp
-constexpr int kNG = 2;               // gamma ring depth (SB): how far the chain may run ahead of the row warps
-
-// Row ring of SA: a multiple of the number of stats warps, so that a stats warp always works on the SAME slots and
-// therefore sees every phase of their mbarriers in order (a parity wait is only sound for a waiter that has
-// observed the previous phase).
-constexpr int kNAs = 4;
-
-struct StreamCfg {
-  int NA, NT;        // ring depths of SB: rows / alpha-table rows
-  int act_bytes;     // bytes per row slot (A*4 rounded up to 128)
-  int tab_bytes;     // bytes per table slot
-  int pitch_max;
-  const int *order;  // CTA -> utterance, longest first
-};
-
-// state pairs per chain thread: 1, 2, 4 or 8 (L + 1 <= 128 * P)
-__device__ __host__ __forceinline__ int stream_pshift(int L) {
-  return L + 1 <= kSChain ? 0 : (L + 1 <= 2 * kSChain ? 1 : (L + 1 <= 4 * kSChain ? 2 : 3));
-}
-
-// The recursion state of one chain thread (P pairs).  ROLE 0: alpha (labels as given), ROLE 1: beta (the same
-// recurrence on the reversed label string, pair i = {Y: state 2(L-i), X: state 2(L-i)-1}).
-template <int P, int ROLE>
-struct Chain {
-  float X[P], Y[P];
-  int lk[P];
-  bool skip[P], hasX[P], hasY[P];
-  float xin, c, xs_prev, cs_prev;
-  bool live, blockend_prev;
-  int rn;
-  __device__ __forceinline__ void init(const int *lab, int L, int tid, int blank) {
-#pragma unroll
-    for (int p = 0; p < P; p++) {
-      const int i = tid * P + p;
-      hasY[p] = i <= L;
-      hasX[p] = i < L;
-      const int li = hasX[p] ? (ROLE ? lab[L - 1 - i] : lab[i]) : blank;
-      const int lprev = (hasX[p] && i >= 1) ? (ROLE ? lab[L - i] : lab[i - 1]) : -1;
-      skip[p] = hasX[p] && i >= 1 && li != lprev;
-      lk[p] = li;
-      X[p] = kNeg;
-      Y[p] = (i == 0) ? 0.f : kNeg;  // virtual frame "-1": all mass on the first blank
-    }
-    xin = kNeg;
-    c = 0.f;
-    xs_prev = kNeg;
-    cs_prev = 0.f;
-    live = (tid == 0);
-    blockend_prev = false;
-    rn = kRenorm;
-  }
-  // what the left neighbour handed over at the end of the previous frame (lane 0 reads the warp-edge word)
-  __device__ __forceinline__ void take_handover(const float2 *bnd_prev, int lane, int wi) {
-    float xv = xs_prev, cv = cs_prev;
-    if (lane == 0) {
-      const float2 v = wi == 0 ? make_float2(kNeg, c) : bnd_prev[wi - 1];
-      xv = v.x;
-      cv = v.y;
-    }
-    if (blockend_prev && !live) c = cv;  // nothing reachable here yet: follow the neighbour's offset
-    xin = fmaxf(xv + (cv - c), kNeg);    // cv - c is an exact integer
-  }
-  __device__ __forceinline__ void step(float Eb, const float (&El)[P]) {
-    float nX[P], nY[P];
-#pragma unroll
-    for (int p = 0; p < P; p++) {
-      const float xp = p == 0 ? xin : X[p - 1];
-      nY[p] = Eb + lse2_2(Y[p], xp);
-      nX[p] = El[p] + lse2_3(X[p], Y[p], skip[p] ? xp : kNeg);
-    }
-#pragma unroll
-    for (int p = 0; p < P; p++) {
-      Y[p] = nY[p];
-      X[p] = nX[p];
-    }
-  }
-  // end of a frame block: re-centre the stored values around this thread's own integer offset
-  __device__ __forceinline__ void recentre() {
-    rn = kRenorm;
-    float mx = kNeg;
-#pragma unroll
-    for (int p = 0; p < P; p++) mx = fmaxf(mx, fmaxf(hasX[p] ? X[p] : kNeg, hasY[p] ? Y[p] : kNeg));
-    live = mx > -1.0e29f;
-    if (live) {
-      const float sh = floorf(mx);
-#pragma unroll
-      for (int p = 0; p < P; p++) {
-        X[p] = fmaxf(X[p] - sh, kNeg);
-        Y[p] = fmaxf(Y[p] - sh, kNeg);
-      }
-      c += sh;
-    }
-  }
-  __device__ __forceinline__ void hand_over(bool block_end, float2 *bnd_cur, int lane, int wi) {
-    xs_prev = __shfl_up_sync(0xffffffffu, X[P - 1], 1);
-    cs_prev = __shfl_up_sync(0xffffffffu, c, 1);
-    if (lane == 31) bnd_cur[wi] = make_float2(X[P - 1], c);
-    blockend_prev = block_end;
-  }
-};
-
-// ---- SA ----------------------------------------------------------------------------------------------
-struct SaSmem {
-  uint64_t *full, *freeb, *lready;   // [NA] each
-  float *l2ring;                     // [NA]
-  float2 *bnd;                       // [2][4]
-  float *fin;                        // [4]
-  unsigned char *ring;
-};
-
-template <int P>
-__device__ __forceinline__ void sa_chain(const CtcDev &d, const UttMeta &um, int b, int tid, const StreamCfg &sc,
-                                         const SaSmem &sm) {
-  const int lane = tid & 31, wi = tid >> 5;
-  const int L = um.L, T = um.T;
-  const int nthreads_needed = (L + 1 + P - 1) / P;
-  Chain<P, 0> ch;
-  ch.init(d.labels + um.lab_off, L, tid, d.blank);
-  const int pitch2 = 2 * um.pitch;
-  float *o = d.alpha + um.ab_off + 2 * tid * P;
-  const int off_stride = (nthreads_needed + 3) & ~3;
-  float *off_out = d.offA + um.off_off + tid;
-  const bool writes_off = tid < nthreads_needed;
-  const bool store_alpha = d.grad != nullptr;
-  PC_DECL;
-  for (int t = 0; t < T; t++) {
-    const int slot = t % kNAs, par = t & 1;
-    const uint32_t ph = (uint32_t)(t / kNAs) & 1u;
-    PC_MARK(7);
-    mbar_wait(sm.lready + slot, ph);   // the row's statistics exist (hence the row has landed)
-    mbar_wait(sm.full + slot, ph);
-    PC_MARK(0);
-    const float *row = reinterpret_cast<const float *>(sm.ring + (size_t)slot * sc.act_bytes);
-    const float l2 = sm.l2ring[slot];
-    if (t > 0) ch.take_handover(sm.bnd + (par ^ 1) * 4, lane, wi);
-    const float Eb = row[d.blank] * kLog2e - l2;
-    float El[P];
-#pragma unroll
-    for (int p = 0; p < P; p++) El[p] = ch.hasX[p] ? row[ch.lk[p]] * kLog2e - l2 : kNeg;
-    __syncwarp();
-    if (lane == 0) mbar_arrive(sm.freeb + slot);  // this warp is done with the row slot
-    PC_MARK(1);
-    ch.step(Eb, El);
-    PC_MARK(2);
-    if (store_alpha) {
-#pragma unroll
-      for (int p = 0; p < P; p++)   // the slot after the last blank is free: it carries the row's log-sum-exp
-        if (ch.hasY[p]) *reinterpret_cast<float2 *>(o + 2 * p) = make_float2(ch.Y[p], ch.hasX[p] ? ch.X[p] : l2);
-      o += pitch2;
-    }
-    const bool block_end = (--ch.rn == 0) || (t == T - 1);
-    if (block_end) {
-      if (writes_off && store_alpha) *off_out = ch.c;   // the offset this frame block was stored with
-      off_out += off_stride;
-      ch.recentre();
-    }
-    ch.hand_over(block_end, sm.bnd + par * 4, lane, wi);
-    PC_MARK(3);
-    named_bar_sync(1, kSChain);   // the warp-edge words of frame t are visible to the neighbours
-    PC_MARK(4);
-  }
-  PC_FLUSH(tid == 0 && blockIdx.x == 0, 0);
-#pragma unroll
-  for (int p = 0; p < P; p++) {
-    const int i = tid * P + p;
-    if (i == L) {
-      sm.fin[0] = ch.Y[p];
-      sm.fin[1] = ch.c;
-    }
-    if (i == L - 1) {
-      sm.fin[2] = ch.X[p];
-      sm.fin[3] = ch.c;
-    }
-  }
-  if (tid == 0 && L == 0) {
-    sm.fin[2] = kNeg;
-    sm.fin[3] = 0.f;
-  }
-  named_bar_sync(1, kSChain);
-  if (tid == 0) {
-    const double v0 = (double)sm.fin[0] + (double)sm.fin[1], v1 = (double)sm.fin[2] + (double)sm.fin[3];
-    const double hi = fmax(v0, v1), lo = fmin(v0, v1);
-    const double lp2 = hi + log2(1.0 + exp2(fmax(lo - hi, -1000.0)));
-    d.logp2[b] = lp2;
-    const float cost = (float)(-lp2 * kLn2);
-    d.costs[b] = cost;
-    if (!(fabsf(cost) < 3.0e38f)) atomicOr(d.flags, 1);
-  }
-}
-
-__global__ void __launch_bounds__(kSThreads, 2) ctc_stream_alpha_kernel(CtcDev d, StreamCfg sc) {
-  extern __shared__ __align__(128) unsigned char ssm[];
-  SaSmem sm;
-  sm.full = reinterpret_cast<uint64_t *>(ssm);
-  sm.freeb = sm.full + 8;
-  sm.lready = sm.freeb + 8;                                   // 3 x 8 barriers = 192 B
-  sm.l2ring = reinterpret_cast<float *>(ssm + 192);            // [8]
-  sm.bnd = reinterpret_cast<float2 *>(ssm + 256);              // [2][4]
-  sm.fin = reinterpret_cast<float *>(ssm + 320);               // [4]
-  sm.ring = ssm + 512;
-
-  const int b = sc.order[blockIdx.x];
-  const UttMeta um = d.meta[b];
-  const bool feasible = um.feasible != 0;
-  if (!feasible && !d.argmax) return;
-  const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
-  const int T = um.T, A = d.A;
-  if (tid == 0) {
-    for (int i = 0; i < kNAs; i++) {
-      mbar_init(sm.full + i, 1);
-      mbar_init(sm.freeb + i, 1 + (feasible ? kSChain / 32 : 0));   // the row's stats warp + the chain warps
-      mbar_init(sm.lready + i, 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (wi == kSC / 32) {
-    if (lane == 0) {  // producer: keeps NA rows of this utterance in flight
-      const uint32_t bytes = (uint32_t)A * 4u;
-      auto issue = [&](int t) {
-        uint64_t *bar = sm.full + t % kNAs;
-        mbar_expect_tx(bar, bytes);
-        tma_load_1d(sm.ring + (size_t)(t % kNAs) * sc.act_bytes, d.act + ((long long)t * d.B + b) * A, bytes, bar);
-      };
-      for (int t = 0; t < min(kNAs, T); t++) issue(t);
-      for (int t = 0; t + kNAs < T; t++) {
-        mbar_wait(sm.freeb + t % kNAs, (uint32_t)(t / kNAs) & 1u);
-        issue(t + kNAs);
-      }
-    }
-    return;
-  }
-  if (wi >= kSChain / 32) {
-    // ===================== stats warps: whole rows, round-robin, ahead of the chain =====================
-    const int sw = wi - kSChain / 32, nsw = (kSC - kSChain) / 32;
-    static_assert(kNAs % ((kSC - kSChain) / 32) == 0, "each stats warp must own a fixed set of ring slots");
-    const int n4 = A >> 2;
-    PC_DECL;
-    for (int t = sw; t < T; t += nsw) {
-      const int slot = t % kNAs;
-      PC_MARK(7);
-      mbar_wait(sm.full + slot, (uint32_t)(t / kNAs) & 1u);
-      PC_MARK(0);
-      const float4 *r4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)slot * sc.act_bytes);
-      // (one warp per row is latency-bound if it runs the online max/rescale recurrence: 3800 cycles per row
-      // measured.  Two straight passes over shared memory -- max, then sum of 2^(x - max) with independent
-      // accumulators and 8 loads in flight -- are throughput-shaped.)
-      float m = -3.0e38f;
-      int am = 0;
-      for (int k0 = lane; k0 < n4; k0 += 256) {
-        float4 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++)
-          v[u] = (k0 + 32 * u < n4) ? r4[k0 + 32 * u] : make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);
-        if (d.argmax) {
-#pragma unroll
-          for (int u = 0; u < 8; u++) {   // ascending indices: the first occurrence of a new maximum wins
-            const float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
-            if (mx > m) {
-              m = mx;
-              const int kk = 4 * (k0 + 32 * u);
-              am = v[u].x == mx ? kk : (v[u].y == mx ? kk + 1 : (v[u].z == mx ? kk + 2 : kk + 3));
-            }
-          }
-        } else {
-          float mx[8];
-#pragma unroll
-          for (int u = 0; u < 8; u++) mx[u] = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w));
-          m = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])), m));
-        }
-      }
-      const float M = warp_max(m);
-      if (d.argmax) {  // smallest index among the lanes that hold the row maximum (FindRowMaxId's tie rule)
-        int cand = m == M ? am : 0x7fffffff;
-#pragma unroll
-        for (int q = 16; q > 0; q >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, q));
-        if (lane == 0) d.argmax[(long long)t * d.B + b] = cand;
-      }
-      const float Ml = M * kLog2e;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int k0 = lane; k0 < n4; k0 += 256) {
-        float4 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++)
-          v[u] = (k0 + 32 * u < n4) ? r4[k0 + 32 * u] : make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          acc[0] += ex2_approx(fmaf(v[u].x, kLog2e, -Ml));
-          acc[1] += ex2_approx(fmaf(v[u].y, kLog2e, -Ml));
-          acc[2] += ex2_approx(fmaf(v[u].z, kLog2e, -Ml));
-          acc[3] += ex2_approx(fmaf(v[u].w, kLog2e, -Ml));
-        }
-      }
-      const float S = warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
-      if (lane == 0) {
-        sm.l2ring[slot] = Ml + log2f(S);
-        mbar_arrive(sm.lready + slot);
-        mbar_arrive(sm.freeb + slot);
-      }
-      PC_MARK(1);
-    }
-    PC_FLUSH(sw == 0 && lane == 0 && blockIdx.x == 0, 8);
-    if (d.argmax)  // padded frames of this utterance
-      for (int t = T + (tid - kSChain); t < d.Tmax; t += kSC - kSChain) d.argmax[(long long)t * d.B + b] = -1;
-    return;
-  }
-  if (!feasible) return;   // (arg-max only: the stats warps do all the work)
-  switch (stream_pshift(um.L)) {
-    case 0: sa_chain<1>(d, um, b, tid, sc, sm); break;
-    case 1: sa_chain<2>(d, um, b, tid, sc, sm); break;
-    case 2: sa_chain<4>(d, um, b, tid, sc, sm); break;
-    default: sa_chain<8>(d, um, b, tid, sc, sm); break;
-  }
-}
-
-// ---- SB ----------------------------------------------------------------------------------------------
-struct SbSmem {
-  uint64_t *full_act, *full_tab, *done_act, *free_tab, *gready, *gfree;
-  float *part;      // [kNG][12]: 4 x z, 4 x z_blank, l2
-  float2 *bnd;      // [2][4]
-  unsigned char *act_base, *tab_base;
-  float *gam;       // [kNG][pitch_max]
-  int *s_us, *s_pos, *s_ul;
-};
-
-template <int P>
-__device__ __forceinline__ void sb_chain(const CtcDev &d, const UttMeta &um, int b, int tid, const StreamCfg &sc,
-                                         const SbSmem &sm) {
-  constexpr int psh = P == 1 ? 0 : (P == 2 ? 1 : (P == 4 ? 2 : 3));
-  const int lane = tid & 31, wi = tid >> 5;
-  const int L = um.L, T = um.T, pitch = um.pitch;
-  Chain<P, 1> ch;
-  ch.init(d.labels + um.lab_off, L, tid, d.blank);
-  const double lp2 = d.logp2[b];
-  const double fl = floor(lp2);
-  const float lp_hi = (float)fl, lp_lo = (float)(lp2 - fl);  // (offset sum - integer part) is exact in fp32
-  // The alpha-table ring is fed by chain thread 0 itself, right after the frame's named barrier (every chain warp is
-  // then past its reads of the slot): a producer loop that also waits for the row warps would hand out table rows at
-  // THEIR pace and starve the chain, which runs up to kNG frames ahead (measured: 830 cycles per frame waiting).
-  const int nstr = ((((L + (1 << psh)) >> psh)) + 3) & ~3;
-  auto issue_tab = [&](int k, int slot) {
-    const int t = T - 1 - k;
-    uint64_t *bar = sm.full_tab + slot;
-    float *dst = reinterpret_cast<float *>(sm.tab_base + (size_t)slot * sc.tab_bytes);
-    mbar_expect_tx(bar, (uint32_t)(2 * pitch + nstr) * 4u);
-    tma_load_1d(dst, d.alpha + um.ab_off + (long long)t * 2 * pitch, (uint32_t)pitch * 8u, bar);
-    tma_load_1d(dst + 2 * pitch, d.offA + um.off_off + (long long)(t / kRenorm) * nstr, (uint32_t)nstr * 4u, bar);
-  };
-  if (tid == 0)
-    for (int k = 0; k < min(sc.NT, T); k++) issue_tab(k, k);
-  // ring positions advance incrementally (NA, NT are run-time values: k % NA costs ~40 instructions a time)
-  int slotA = 0, slotT = 0, slotG = 0;
-  uint32_t phA = 0, phT = 0, phG = 0;
-  PC_DECL;
-  for (int k = 0; k < T; k++) {
-    const int par = k & 1;
-    const float *arow = reinterpret_cast<const float *>(sm.act_base + (size_t)slotA * sc.act_bytes);
-    const float *tab = reinterpret_cast<const float *>(sm.tab_base + (size_t)slotT * sc.tab_bytes);
-    const float *oa = tab + 2 * pitch;   // alpha's per-thread offsets of this frame block
-    float *gam = sm.gam + slotG * sc.pitch_max;
-    PC_MARK(7);
-    if (k >= kNG) mbar_wait(sm.gfree + slotG, phG ^ 1u);   // the row warps released this gamma slot
-    PC_MARK(0);
-    mbar_wait(sm.full_tab + slotT, phT);
-    PC_MARK(1);
-    mbar_wait(sm.full_act + slotA, phA);
-    PC_MARK(2);
-    const float l2 = tab[2 * L + 1];     // the row's base-2 log-sum-exp, left there by SA
-    if (k > 0) ch.take_handover(sm.bnd + (par ^ 1) * 4, lane, wi);
-    const float Eb = arow[d.blank] * kLog2e - l2;
-    float El[P];
-#pragma unroll
-    for (int p = 0; p < P; p++) El[p] = ch.hasX[p] ? arow[ch.lk[p]] * kLog2e - l2 : kNeg;
-    // alpha of my states and the offsets they were stored with: loaded before the recursion step, used after it
-    float aY[P], aX[P], oY[P], oX[P];
-#pragma unroll
-    for (int p = 0; p < P; p++) {
-      const int i = tid * P + p;
-      const int sY = ch.hasY[p] ? 2 * (L - i) : 0;
-      aY[p] = tab[sY];
-      oY[p] = oa[ch.hasY[p] ? (L - i) >> psh : 0];
-      aX[p] = ch.hasX[p] ? tab[sY - 1] : 0.f;
-      oX[p] = ch.hasX[p] ? oa[(L - i - 1) >> psh] : 0.f;
-    }
-    ch.step(Eb, El);
-    PC_MARK(3);
-    // state posteriors gamma_t(s) ~ 2^(alpha + beta - E + offsets - log2 p), straight from the registers
-    float z = 0.f, zblank = 0.f;
-    const float cb = ch.c - lp_hi;
-#pragma unroll
-    for (int p = 0; p < P; p++) {
-      const int i = tid * P + p;
-      if (ch.hasY[p]) {
-        const float v0 = ex2_approx(fminf(fmaxf((aY[p] + ch.Y[p] - Eb) + ((oY[p] + cb) - lp_lo), -200.f), 100.f));
-        zblank += v0;
-        if (ch.hasX[p]) {
-          const float v1 = ex2_approx(fminf(fmaxf((aX[p] + ch.X[p] - El[p]) + ((oX[p] + cb) - lp_lo), -200.f), 100.f));
-          z += v1;
-          gam[L - 1 - i] = v1;   // label position L-1-i
-        }
-      }
-    }
-    z += zblank;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {   // the two sums share the shuffle rounds
-      z += __shfl_xor_sync(0xffffffffu, z, o);
-      zblank += __shfl_xor_sync(0xffffffffu, zblank, o);
-    }
-    if (lane == 0) {
-      sm.part[slotG * 12 + wi] = z;
-      sm.part[slotG * 12 + 4 + wi] = zblank;
-      if (wi == 0) sm.part[slotG * 12 + 8] = l2;
-      mbar_arrive(sm.gready + slotG);     // release: this warp's gam[] / part[] writes and its gathers from the raw row
-    }
-    PC_MARK(4);
-    const bool block_end = (--ch.rn == 0) || (k == T - 1);
-    if (block_end) ch.recentre();
-    ch.hand_over(block_end, sm.bnd + par * 4, lane, wi);
-    named_bar_sync(1, kSChain);
-    if (tid == 0 && k + sc.NT < T) issue_tab(k + sc.NT, slotT);   // every chain warp is past this table slot
-    PC_MARK(5);
-    if (++slotA == sc.NA) { slotA = 0; phA ^= 1u; }
-    if (++slotT == sc.NT) { slotT = 0; phT ^= 1u; }
-    if (++slotG == kNG) { slotG = 0; phG ^= 1u; }
-  }
-  PC_FLUSH(tid == 0 && blockIdx.x == 0, 16);
-}
-
-__device__ __forceinline__ void sb_rows(const CtcDev &d, const UttMeta &um, int rt, const StreamCfg &sc,
-                                        const SbSmem &sm, int nuniq) {
-  constexpr int NR = kSC - kSChain;   // row threads
-  const int lane = rt & 31;
-  const int T = um.T, n4 = d.A >> 2;
-  const float gs = d.grad_scale;
-  int slotA = 0, slotG = 0;
-  uint32_t phA = 0, phG = 0;
-  PC_DECL;
-  for (int k = 0; k < T; k++) {
-    float *arow = reinterpret_cast<float *>(sm.act_base + (size_t)slotA * sc.act_bytes);
-    const float *gam = sm.gam + slotG * sc.pitch_max;
-    PC_MARK(7);
-    mbar_wait(sm.gready + slotG, phG);      // gamma of frame k is complete, the raw row is no longer needed
-    mbar_wait(sm.full_act + slotA, phA);
-    PC_MARK(0);
-    const float *part = sm.part + slotG * 12;
-    const float Z = (part[0] + part[1]) + (part[2] + part[3]);
-    const float zb = (part[4] + part[5]) + (part[6] + part[7]);
-    const float l2 = part[8];
-    const float invZ = Z > 0.f ? 1.0f / Z : 0.f;
-    if (rt == 0 && !(Z > 0.f && Z < 3.0e38f)) atomicOr(d.flags, 2);   // no usable posterior for this frame
-    // ---- y = grad_scale * softmax(row), in place in the row slot: eight 16-byte loads in flight per thread
-    float4 *a4 = reinterpret_cast<float4 *>(arow);
-    for (int k0 = rt; k0 < n4; k0 += 8 * NR) {
-      float4 v[8];
-#pragma unroll
-      for (int u = 0; u < 8; u++)
-        if (k0 + u * NR < n4) v[u] = a4[k0 + u * NR];
-#pragma unroll
-      for (int u = 0; u < 8; u++)
-        if (k0 + u * NR < n4) {
-          v[u].x = gs * ex2_approx(fmaf(v[u].x, kLog2e, -l2));
-          v[u].y = gs * ex2_approx(fmaf(v[u].y, kLog2e, -l2));
-          v[u].z = gs * ex2_approx(fmaf(v[u].z, kLog2e, -l2));
-          v[u].w = gs * ex2_approx(fmaf(v[u].w, kLog2e, -l2));
-          a4[k0 + u * NR] = v[u];
-        }
-    }
-    PC_MARK(1);
-    named_bar_sync(2, NR);  // the scaled row is complete
-    PC_MARK(2);
-    // ---- subtract the posterior mass of every distinct label (fixed summation order) and of the blank;
-    //      four labels per thread in flight (the chain of dependent shared-memory loads is what costs here)
-    const float gz = gs * invZ;
-    for (int j0 = rt; j0 < nuniq; j0 += 4 * NR) {
-      int q0[4], q1[4], sym[4];
-      float acc[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int j = j0 + u * NR;
-        const bool ok = j < nuniq;
-        q0[u] = ok ? sm.s_us[j] : 0;
-        q1[u] = ok ? sm.s_us[j + 1] : 0;
-        sym[u] = ok ? sm.s_ul[j] : 0;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) acc[u] = q1[u] > q0[u] ? gam[sm.s_pos[q0[u]]] : 0.f;
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-        for (int q = q0[u] + 1; q < q1[u]; q++) acc[u] += gam[sm.s_pos[q]];
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-        if (j0 + u * NR < nuniq) arow[sym[u]] -= gz * acc[u];
-    }
-    if (rt == 0) arow[d.blank] -= gz * zb;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk store
-    __syncwarp();
-    if (lane == 0) {
-      mbar_arrive(sm.done_act + slotA);
-      mbar_arrive(sm.gfree + slotG);
-    }
-    PC_MARK(3);
-    if (++slotA == sc.NA) { slotA = 0; phA ^= 1u; }
-    if (++slotG == kNG) { slotG = 0; phG ^= 1u; }
-  }
-  PC_FLUSH(rt == 0 && blockIdx.x == 0, 24);
-}
-
-__global__ void __launch_bounds__(kSThreads, 2) ctc_stream_beta_grad_kernel(CtcDev d, StreamCfg sc) {
-  extern __shared__ __align__(128) unsigned char ssm[];
-  SbSmem sm;
-  sm.full_act = reinterpret_cast<uint64_t *>(ssm);   // [NA <= 8]
-  sm.done_act = sm.full_act + 8;                      // [NA]
-  sm.full_tab = sm.done_act + 8;                      // [NT <= 4]
-  sm.free_tab = sm.full_tab + 4;                      // [NT]
-  sm.gready = sm.free_tab + 4;                        // [kNG <= 4]
-  sm.gfree = sm.gready + 4;                           // [kNG]            32 barriers = 256 B
-  sm.part = reinterpret_cast<float *>(ssm + 256);     // [kNG][12]
-  sm.bnd = reinterpret_cast<float2 *>(ssm + 448);     // [2][4]
-  sm.act_base = ssm + 512;
-  sm.tab_base = sm.act_base + (size_t)sc.NA * sc.act_bytes;
-  sm.gam = reinterpret_cast<float *>(sm.tab_base + (size_t)sc.NT * sc.tab_bytes);
-  sm.s_us = reinterpret_cast<int *>(sm.gam + kNG * sc.pitch_max);   // [pitch_max + 4]
-  sm.s_pos = sm.s_us + sc.pitch_max + 4;                            // [pitch_max]
-  sm.s_ul = sm.s_pos + sc.pitch_max;                                // [pitch_max]
-
-  const int b = sc.order[blockIdx.x];
-  const UttMeta um = d.meta[b];
-  const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
-  const int A = d.A, T = um.feasible ? um.T : 0;
-  if (tid == 0) {
-    for (int i = 0; i < sc.NA; i++) {
-      mbar_init(sm.full_act + i, 1);
-      mbar_init(sm.done_act + i, (kSC - kSChain) / 32);
-    }
-    for (int i = 0; i < sc.NT; i++) {
-      mbar_init(sm.full_tab + i, 1);
-      mbar_init(sm.free_tab + i, kSChain / 32);   // (unused since the chain feeds the table ring itself)
-    }
-    for (int i = 0; i < kNG; i++) {
-      mbar_init(sm.gready + i, kSChain / 32);
-      mbar_init(sm.gfree + i, (kSC - kSChain) / 32);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (wi == kSC / 32) {
-    if (lane == 0 && T > 0) {
-      // ============ producer: keeps the row ring full and drains finished rows (time runs backwards);
-      //              the alpha-table ring is fed by the chain (see sb_chain) ============
-      const uint32_t row_bytes = (uint32_t)A * 4u;
-      auto issue_act = [&](int k, int slot) {
-        const int t = T - 1 - k;
-        uint64_t *bar = sm.full_act + slot;
-        mbar_expect_tx(bar, row_bytes);
-        tma_load_1d(sm.act_base + (size_t)slot * sc.act_bytes, d.act + ((long long)t * d.B + b) * A, row_bytes, bar);
-      };
-      for (int k = 0; k < min(sc.NA - 1, T); k++) issue_act(k, k);
-      int slot = 0, nslot = sc.NA - 1;   // slot of row k / of row k + NA - 1
-      uint32_t ph = 0;
-      PC_DECL;
-      for (int k = 0; k < T; k++) {
-        PC_MARK(7);
-        mbar_wait(sm.done_act + slot, ph);  // row k finished in its slot
-        PC_MARK(1);
-        bulk_store(d.grad + ((long long)(T - 1 - k) * d.B + b) * A, sm.act_base + (size_t)slot * sc.act_bytes, row_bytes);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        // the slot of row k-1 (its store was committed one row ago) takes row k+NA-1
-        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        PC_MARK(2);
-        if (k + sc.NA - 1 < T) issue_act(k + sc.NA - 1, nslot);
-        if (++slot == sc.NA) { slot = 0; ph ^= 1u; }
-        if (++nslot == sc.NA) nslot = 0;
-      }
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      PC_FLUSH(blockIdx.x == 0, 32);
-    }
-    return;
-  }
-  if (T > 0) {
-    if (wi >= kSChain / 32) {
-      // row warps: the utterance's label -> positions CSR into shared memory, then the row loop
-      const int rt = tid - kSChain, nrt = kSC - kSChain;
-      const int nuniq = d.nuniq[b];
-      const int *ul = d.uniq_lab + um.csr_off, *us = d.uniq_start + um.csr_off + b, *pos = d.pos + um.lab_off;
-      for (int k = rt; k <= nuniq; k += nrt) sm.s_us[k] = us[k];
-      for (int k = rt; k < nuniq; k += nrt) sm.s_ul[k] = ul[k];
-      for (int k = rt; k < um.L; k += nrt) sm.s_pos[k] = pos[k];
-      named_bar_sync(2, nrt);
-      sb_rows(d, um, rt, sc, sm, nuniq);
-    } else {
-      switch (stream_pshift(um.L)) {
-        case 0: sb_chain<1>(d, um, b, tid, sc, sm); break;
-        case 1: sb_chain<2>(d, um, b, tid, sc, sm); break;
-        case 2: sb_chain<4>(d, um, b, tid, sc, sm); break;
-        default: sb_chain<8>(d, um, b, tid, sc, sm); break;
-      }
-    }
-  }
-  // ---- zero rows: padded frames (all frames of an unalignable utterance)
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int t = T; t < d.Tmax; t++) {
-    float4 *g4 = reinterpret_cast<float4 *>(d.grad + ((long long)t * d.B + b) * A);
-    for (int k = tid; k < (A >> 2); k += kSC) g4[k] = zero4;
-  }
-}
-
-// ===========================================================================
 // host side
 // ===========================================================================
 struct Plan {
   int A, B, Tmax, maxL, pitch_max;
   long long sumT, sumL;
-  size_t off_meta, off_order, off_labels, off_uniq_lab, off_uniq_start, off_pos, off_nuniq;  // header block
+  size_t off_meta, off_labels, off_uniq_lab, off_uniq_start, off_pos, off_nuniq;  // header block
   size_t header_bytes;
   size_t off_lse2, off_E, off_alpha, off_beta, off_offA, off_offB, off_logp2, off_costs, off_flags;
   size_t total;
@@ -1546,7 +897,6 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int A,
   if (p->maxL + 1 > 512 * 4) return CTC_STATUS_INVALID_VALUE;  // P <= 4, 512 threads per direction
   size_t o = 0;
   p->off_meta = o;        o = align_up(o + sizeof(UttMeta) * B, 256);
-  p->off_order = o;       o = align_up(o + sizeof(int) * B, 256);
   p->off_labels = o;      o = align_up(o + sizeof(int) * (p->sumL + 1), 256);
   p->off_uniq_lab = o;    o = align_up(o + sizeof(int) * (p->sumL + 1), 256);
   p->off_uniq_start = o;  o = align_up(o + sizeof(int) * (p->sumL + B + 1), 256);
@@ -1578,7 +928,7 @@ struct Staging {
 
 // Tuning switches: read from the environment ONCE per process (none is needed in production).
 struct Tuning {
-  int force_p, ring, na, nt, profile, groups, one_stream, stream_path, stream_na;
+  int force_p, ring, na, nt, profile, groups, one_stream;
 };
 const Tuning &tuning() {
   static const Tuning t = [] {
@@ -1591,8 +941,6 @@ const Tuning &tuning() {
     v.profile = geti("B200CTC_PROFILE", 0);
     v.groups = geti("B200CTC_GROUPS", 0);
     v.one_stream = geti("B200CTC_ONE_STREAM", 0);
-    v.stream_path = geti("B200CTC_STREAM", -1);   // 0 / 1: never / whenever possible use the streaming path
-    v.stream_na = geti("B200CTC_STREAM_NA", 0);
     return v;
   }();
   return t;
@@ -1605,7 +953,7 @@ constexpr int kMaxGroups = 8;
 struct DeviceState {
   int num_sms = 0;
   bool k2_attr[3] = {false, false, false};   // P = 1, 2, 4
-  size_t smem3_set = 0, ring_set = 0, sa_set = 0, sb_set = 0;
+  size_t smem3_set = 0, ring_set = 0;
   cudaStream_t hp[kMaxGroups] = {};
   cudaEvent_t e1[kMaxGroups] = {}, e2[kMaxGroups] = {};
   Staging stage;
@@ -1640,30 +988,6 @@ bool ensure_pinned(Staging &s, size_t bytes, size_t ncosts) {
     s.costs_cap = ncosts * 2;
   }
   return true;
-}
-
-// costs / flag word out; synchronise unless the caller asked not to
-ctcStatus_t finish_call(const CtcDev &dev, int B, float *costs_host, float *costs_dev, const b200ctcOptions &opt,
-                        cudaStream_t stream, Staging &g_stage) {
-  if (costs_dev &&
-      cudaMemcpyAsync(costs_dev, dev.costs, sizeof(float) * B, cudaMemcpyDeviceToDevice, stream) !=
-          cudaSuccess)
-    return CTC_STATUS_MEMOPS_FAILED;
-  if (opt.nonfinite_dev &&
-      cudaMemcpyAsync(opt.nonfinite_dev, dev.flags, sizeof(int), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
-    return CTC_STATUS_MEMOPS_FAILED;
-  if (!opt.no_sync) {
-    if (cudaMemcpyAsync(g_stage.costs, dev.costs, sizeof(float) * B, cudaMemcpyDeviceToHost,
-                        stream) != cudaSuccess)
-      return CTC_STATUS_MEMOPS_FAILED;
-    cudaError_t e = cudaStreamSynchronize(stream);
-    if (e != cudaSuccess) {
-      fprintf(stderr, "b200ctc: %s\n", cudaGetErrorString(e));
-      return CTC_STATUS_EXECUTION_FAILED;
-    }
-    if (costs_host) memcpy(costs_host, g_stage.costs, sizeof(float) * B);
-  }
-  return CTC_STATUS_SUCCESS;
 }
 
 template <int P>
@@ -1731,11 +1055,6 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
     m.vrow0 = vrows_total;
     if (m.feasible) vrows_total += m.T;
     hm[b] = m;
-  }
-  {  // CTA -> utterance map of the streaming kernels: longest utterances first (they bound the run time)
-    int *ho = reinterpret_cast<int *>(h + p.off_order);
-    for (int b = 0; b < B; b++) ho[b] = b;
-    std::stable_sort(ho, ho + B, [&](int x, int y) { return p.meta[x].T > p.meta[y].T; });
   }
   unsigned char *w = static_cast<unsigned char *>(workspace);
   if (cudaMemcpyAsync(w, h, p.off_uniq_lab, cudaMemcpyHostToDevice, stream) != cudaSuccess)
@@ -1810,13 +1129,6 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   dev.costs = reinterpret_cast<float *>(w + p.off_costs);
   dev.flags = reinterpret_cast<int *>(w + p.off_flags);
   dev.argmax = opt.argmax_dev;
-  dev.pc = nullptr;
-#ifdef B200CTC_PHASE_COUNTERS
-  static long long *pc_dev = nullptr;
-  if (!pc_dev) cudaMalloc(&pc_dev, 64 * sizeof(long long));
-  cudaMemsetAsync(pc_dev, 0, 64 * sizeof(long long), stream);
-  dev.pc = pc_dev;
-#endif
 
   // K2 geometry: P pairs per thread so that one direction fits 512 threads
   const int npairs = p.maxL + 1;
@@ -1869,86 +1181,6 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
                                (int)ring_smem) != cudaSuccess)
         return CTC_STATUS_EXECUTION_FAILED;
       ring_set = ring_smem;
-    }
-  }
-  // ---- streaming path: one persistent CTA per utterance, the recursions ride the two slab reads
-  {
-    StreamCfg sc;
-    sc.act_bytes = (int)align_up((size_t)A * 4, 128);
-    sc.tab_bytes = (int)align_up((size_t)3 * p.pitch_max * 4, 128);
-    sc.pitch_max = p.pitch_max;
-    sc.order = reinterpret_cast<const int *>(w + p.off_order);
-    sc.NT = 2;
-    sc.NA = tune.stream_na >= 3 && tune.stream_na <= 8 ? tune.stream_na : 6;   // (SB; SA's ring is kNAs)
-    auto sb_bytes = [&]() {
-      return (size_t)512 + (size_t)sc.NA * sc.act_bytes + (size_t)sc.NT * sc.tab_bytes +
-             sizeof(float) * ((size_t)(kNG + 3) * p.pitch_max + 8);
-    };
-    while (sb_bytes() > ((size_t)113 << 10) && sc.NA > 3) sc.NA--;   // two CTAs per SM when the rows allow it
-    const size_t sb_smem = sb_bytes(), sa_smem = (size_t)512 + (size_t)kNAs * sc.act_bytes;
-    const bool slab_big = (size_t)p.Tmax * B * A >= ((size_t)64 << 20);
-    bool use_stream = (A & 3) == 0 && A >= 1024 && slab_big && B >= 96 && p.maxL + 1 <= 8 * kSChain &&
-                      sb_smem <= ((size_t)220 << 10) && (uintptr_t)act % 16 == 0 && (uintptr_t)grad % 16 == 0;
-    if (tune.stream_path != 1) use_stream = false;   // (not yet the default: slower than the three-kernel path, see profiles/)
-    if (tune.stream_path == 1)
-      use_stream = (A & 3) == 0 && p.maxL + 1 <= 8 * kSChain && sb_smem <= ((size_t)220 << 10) &&
-                   (uintptr_t)act % 16 == 0 && (uintptr_t)grad % 16 == 0;
-    if (use_stream) {
-      if (sa_smem > ds->sa_set) {
-        if (cudaFuncSetAttribute(ctc_stream_alpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa_smem) !=
-            cudaSuccess)
-          return CTC_STATUS_EXECUTION_FAILED;
-        ds->sa_set = sa_smem;
-      }
-      if (grad && sb_smem > ds->sb_set) {
-        if (cudaFuncSetAttribute(ctc_stream_beta_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sb_smem) != cudaSuccess)
-          return CTC_STATUS_EXECUTION_FAILED;
-        ds->sb_set = sb_smem;
-      }
-      dev.b_lo = 0;
-      dev.nb = B;
-      cudaEvent_t sev[3];
-      const bool sprof = tune.profile == 1;
-      if (sprof) {
-        for (int i = 0; i < 3; i++) cudaEventCreate(&sev[i]);
-        cudaEventRecord(sev[0], stream);
-      }
-      ctc_stream_alpha_kernel<<<B, kSThreads, sa_smem, stream>>>(dev, sc);
-      if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
-      if (sprof) cudaEventRecord(sev[1], stream);
-      if (grad) {
-        if (!build_and_upload_csr()) return CTC_STATUS_MEMOPS_FAILED;   // host work under the alpha kernel
-        ctc_stream_beta_grad_kernel<<<B, kSThreads, sb_smem, stream>>>(dev, sc);
-        if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
-      } else {
-        cudaEventRecord(g_stage.copied, stream);
-        g_stage.pending = true;
-      }
-      if (sprof) {
-        cudaEventRecord(sev[2], stream);
-        cudaEventSynchronize(sev[2]);
-        float t1 = 0, t2 = 0;
-        cudaEventElapsedTime(&t1, sev[0], sev[1]);
-        cudaEventElapsedTime(&t2, sev[1], sev[2]);
-        fprintf(stderr, "[b200ctc] streaming path B=%d A=%d Tmax=%d maxL=%d NA=%d: alpha %.3f ms, beta+grad %.3f ms\n", B, A,
-                p.Tmax, p.maxL, sc.NA, t1, t2);
-        for (int i = 0; i < 3; i++) cudaEventDestroy(sev[i]);
-#ifdef B200CTC_PHASE_COUNTERS
-        long long h[64];
-        cudaMemcpy(h, dev.pc, sizeof(h), cudaMemcpyDeviceToHost);
-        const double n = p.meta[reinterpret_cast<const int *>(g_stage.pinned + p.off_order)[0]].T;
-        fprintf(stderr, "[b200ctc pc] CTA 0 (T=%.0f), cycles per frame\n  SA chain: wait %.0f gather %.0f step %.0f store+handover %.0f barrier %.0f loop %.0f\n"
-                "  SA stats(per own row): wait %.0f work %.0f loop %.0f\n"
-                "  SB chain: wait_gfree %.0f wait_tab %.0f wait_act %.0f gather+step %.0f gamma+sums %.0f handover+barrier %.0f loop %.0f\n"
-                "  SB rows: wait %.0f softmax %.0f barrier %.0f fixup+fence+arrive %.0f loop %.0f\n"
-                "  SB producer: tab %.0f wait_done %.0f store+wait_read %.0f loop %.0f\n",
-                n, h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[7] / n, h[8] / n * 4, h[9] / n * 4, h[15] / n * 4,
-                h[16] / n, h[17] / n, h[18] / n, h[19] / n, h[20] / n, h[21] / n, h[23] / n,
-                h[24] / n, h[25] / n, h[26] / n, h[27] / n, h[31] / n, h[32] / n, h[33] / n, h[34] / n, h[39] / n);
-#endif
-      }
-      return finish_call(dev, B, costs_host, costs_dev, opt, stream, g_stage);
     }
   }
   // tuning aid: B200CTC_PROFILE=1 serialises the groups and prints the duration of each kernel
@@ -2064,7 +1296,25 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
     }
     cudaEventDestroy(tl0);
   }
-  return finish_call(dev, B, costs_host, costs_dev, opt, stream, g_stage);
+  if (costs_dev &&
+      cudaMemcpyAsync(costs_dev, dev.costs, sizeof(float) * B, cudaMemcpyDeviceToDevice, stream) !=
+          cudaSuccess)
+    return CTC_STATUS_MEMOPS_FAILED;
+  if (opt.nonfinite_dev &&
+      cudaMemcpyAsync(opt.nonfinite_dev, dev.flags, sizeof(int), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+    return CTC_STATUS_MEMOPS_FAILED;
+  if (!opt.no_sync) {
+    if (cudaMemcpyAsync(g_stage.costs, dev.costs, sizeof(float) * B, cudaMemcpyDeviceToHost,
+                        stream) != cudaSuccess)
+      return CTC_STATUS_MEMOPS_FAILED;
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+      fprintf(stderr, "b200ctc: %s\n", cudaGetErrorString(e));
+      return CTC_STATUS_EXECUTION_FAILED;
+    }
+    if (costs_host) memcpy(costs_host, g_stage.costs, sizeof(float) * B);
+  }
+  return CTC_STATUS_SUCCESS;
 }
 
 }  // namespace

@@ -3,7 +3,6 @@
 // of forward / backward-data / backward-weights.  Replaces what
 // CuDNNRecurrentComponent gets from cuDNN 5 (src/nnet2/nnet-cudnn-component.cc
 // :100-315 descriptors, :534-555 forward, :576-599 backward).
-#include <cuda_bf16.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -28,12 +27,9 @@ struct b200rnnPlan_st {
   int launches;
   // reserve layout (floats), per layer
   std::vector<size_t> r_gates[2], r_cell[2], r_y, r_bias;
-  std::vector<size_t> r_y16, r_dg16[2];   // BF16 copies (tensor mode): layer outputs, input-side gate gradients
-  size_t w_x16, w_w16;                    // workspace: BF16 copy of the input (when the caller has none), of W_i / W_i^T
-  bool bf16_gemms;                        // tensor mode with the tcgen05 recurrent kernels: projections / dx run kind::f16
   bool tc_bwd_used;  // the last BackwardData left fused bias gradients in the reserve
   // tuning switches, read from the environment ONCE when the plan is created
-  bool force_stream, tc_no_bwd, phase_counters, no_bf16;
+  bool force_stream, tc_no_bwd, phase_counters;
   int force_bc;
   size_t reserve_floats;
   // workspace layout (floats)
@@ -41,8 +37,8 @@ struct b200rnnPlan_st {
   size_t splitk_floats, colsum_floats;
   // optional event timing: [category] -> recorded (start, stop) pairs
   bool profiling;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];
-  size_t ev_used[3];
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[4];
+  size_t ev_used[4];
 };
 
 namespace {
@@ -62,8 +58,6 @@ b200rnnStatus_t ensure_geometry(b200rnnPlan_st *p) {
     p->tcBC = rec_tc_pick_chunk(p->H, p->B, p->dirs);
     if (p->force_bc) p->tcBC = p->force_bc;  // tuning override: 4, 8 or 16
   }
-  // BF16 operand copies exist only where the tcgen05 recurrent kernels produce them
-  p->bf16_gemms = p->tcNC != 0 && !p->no_bf16;
   p->geometry_ready = true;
   return B200RNN_STATUS_SUCCESS;
 }
@@ -94,49 +88,6 @@ __global__ void update_kernel(float *w, float *delta, const float *dw, size_t n,
       w[i] = fmaf(lr, g, w[i]);
     }
   }
-}
-
-// fp32 -> BF16 (round to nearest even), contiguous
-__global__ void to_bf16_kernel(const float *src, __nv_bfloat16 *dst, size_t n4) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 v = reinterpret_cast<const float4 *>(src)[i];
-    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-    reinterpret_cast<uint2 *>(dst)[i] =
-        make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
-  }
-}
-// W [R x C] fp32 -> W^T [C x R] BF16 (32 x 32 tiles through shared memory); blockIdx.z = direction
-__global__ void transpose_to_bf16_kernel(const float *w0, const float *w1, __nv_bfloat16 *dst, int R, int C) {
-  __shared__ float tile[32][33];
-  const float *w = blockIdx.z ? w1 : w0;
-  __nv_bfloat16 *o = dst + (size_t)blockIdx.z * R * C;
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < R && c < C) ? w[(size_t)r * C + c] : 0.f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = c0 + i, r = r0 + threadIdx.x;
-    if (c < C && r < R) o[(size_t)c * R + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
-  }
-}
-// the same for two equally sized blocks (the W_i of both directions) in one launch: blockIdx.y picks the block
-__global__ void to_bf16_pair_kernel(const float *s0, const float *s1, __nv_bfloat16 *dst, size_t n4) {
-  const float *src = blockIdx.y ? s1 : s0;
-  __nv_bfloat16 *o = dst + (size_t)blockIdx.y * n4 * 4;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 v = reinterpret_cast<const float4 *>(src)[i];
-    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-    reinterpret_cast<uint2 *>(o)[i] =
-        make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
-  }
-}
-cudaError_t to_bf16(const float *src, void *dst, size_t n, cudaStream_t stream) {   // n % 4 == 0, 16-byte aligned
-  if (n == 0) return cudaSuccess;
-  const unsigned grid = (unsigned)std::min<size_t>((n / 4 + 255) / 256, 148 * 8);
-  to_bf16_kernel<<<grid, 256, 0, stream>>>(src, static_cast<__nv_bfloat16 *>(dst), n / 4);
-  return cudaGetLastError();
 }
 
 // one warp per row: scale rows whose L2 norm exceeds thr down to thr
@@ -229,7 +180,6 @@ b200rnnStatus_t b200rnnCreatePlan(b200rnnPlan_t *plan, b200rnnMode_t mode, int b
   p->profiling = false;
   p->force_stream = getenv("B200RNN_FORCE_STREAM") != nullptr;
   p->tc_no_bwd = getenv("B200RNN_TC_NO_BWD") != nullptr;
-  p->no_bf16 = getenv("B200RNN_NO_BF16_GEMM") != nullptr;   // tuning aid: keep every GEMM on TF32 from fp32 operands
 #ifdef B200RNN_PHASE_COUNTERS
   p->phase_counters = getenv("B200RNN_TC_PROFILE") != nullptr;
 #else
@@ -240,7 +190,7 @@ b200rnnStatus_t b200rnnCreatePlan(b200rnnPlan_t *plan, b200rnnMode_t mode, int b
     const int v = atoi(e);
     if (v == 4 || v == 8 || v == 16) p->force_bc = v;
   }
-  p->ev_used[0] = p->ev_used[1] = p->ev_used[2] = 0;
+  p->ev_used[0] = p->ev_used[1] = p->ev_used[2] = p->ev_used[3] = 0;
   // blob: all matrices of all pseudo-layers, then all biases
   const int npl = p->layers * p->dirs;
   p->pl.resize(npl);
@@ -269,10 +219,6 @@ b200rnnStatus_t b200rnnCreatePlan(b200rnnPlan_t *plan, b200rnnMode_t mode, int b
   }
   p->r_y.assign(p->layers, 0);
   p->r_bias.assign(p->layers, 0);
-  p->r_y16.assign(p->layers, 0);
-  p->r_dg16[0].assign(p->layers, 0);
-  p->r_dg16[1].assign(p->layers, 0);
-  p->bf16_gemms = false;
   p->tc_bwd_used = false;
   for (int l = 0; l < p->layers; l++) {
     for (int d = 0; d < p->dirs; d++) {
@@ -287,16 +233,6 @@ b200rnnStatus_t b200rnnCreatePlan(b200rnnPlan_t *plan, b200rnnMode_t mode, int b
     }
     p->r_bias[l] = r;  // [chunks of 4 utterances][dirs][2][GH]
     r = align_up(r + (size_t)((p->B + 3) / 4) * p->dirs * 2 * p->GH, 64);
-    if (p->math == 1) {   // BF16 copies (2 bytes per element, counted in floats)
-      for (int d = 0; d < p->dirs; d++) {
-        p->r_dg16[d][l] = r;
-        r = align_up(r + (TB * p->GH + 1) / 2, 64);
-      }
-      if (l + 1 < p->layers) {
-        p->r_y16[l] = r;
-        r = align_up(r + (TB * p->HO + 1) / 2, 64);
-      }
-    }
   }
   p->reserve_floats = r;
   // workspace
@@ -320,13 +256,6 @@ b200rnnStatus_t b200rnnCreatePlan(b200rnnPlan_t *plan, b200rnnMode_t mode, int b
   }
   p->w_stream = w;
   w = align_up(w + rec_stream_scratch_floats(p->dirs, p->B, p->H), 64);
-  p->w_x16 = p->w_w16 = w;
-  if (p->math == 1) {
-    p->w_x16 = w;
-    w = align_up(w + (TB * (size_t)p->D + 1) / 2, 64);           // only the plan's own input can lack a BF16 copy
-    p->w_w16 = w;
-    w = align_up(w + ((size_t)p->dirs * p->GH * maxin + 1) / 2, 64);
-  }
   p->workspace_floats = w;
   *plan = p;
   return B200RNN_STATUS_SUCCESS;
@@ -334,7 +263,7 @@ b200rnnStatus_t b200rnnCreatePlan(b200rnnPlan_t *plan, b200rnnMode_t mode, int b
 
 b200rnnStatus_t b200rnnDestroyPlan(b200rnnPlan_t plan) {
   if (plan)
-    for (int c = 0; c < 3; c++)
+    for (int c = 0; c < 4; c++)
       for (auto &e : plan->ev[c]) {
         cudaEventDestroy(e.first);
         cudaEventDestroy(e.second);
@@ -383,12 +312,6 @@ b200rnnStatus_t b200rnnGetReserveSize(b200rnnPlan_t p, size_t *bytes) {
 
 b200rnnStatus_t b200rnnForward(b200rnnPlan_t p, int T, const float *x, const float *w, float *y,
                                void *workspace, void *reserve, b200rnnStream_t stream_) {
-  return b200rnnForwardEx(p, T, x, nullptr, w, y, nullptr, workspace, reserve, stream_);
-}
-
-b200rnnStatus_t b200rnnForwardEx(b200rnnPlan_t p, int T, const float *x, const void *x_bf16, const float *w,
-                                 float *y, void *y_bf16, void *workspace, void *reserve,
-                                 b200rnnStream_t stream_) {
   if (!p || !x || !w || !y || !workspace || T < 1 || T > p->Tmax) return B200RNN_STATUS_INVALID_VALUE;
   b200rnnStatus_t gs = ensure_geometry(p);
   if (gs != B200RNN_STATUS_SUCCESS) return gs;
@@ -404,32 +327,6 @@ b200rnnStatus_t b200rnnForwardEx(b200rnnPlan_t p, int T, const float *x, const v
     a.mode = p->mode; a.T = T; a.B = p->B; a.H = p->H; a.dirs = p->dirs;
     a.NC = p->NC; a.U = p->NC ? p->H / p->NC : 0; a.BC = p->BC;
     a.y = out; a.dy = nullptr; a.save = rs ? 1 : 0;
-    // BF16 operands for the hoisted projection (tensor mode): the input's BF16 copy -- the caller's, the previous
-    // layer's (written by its recurrent kernel), or one made here -- and BF16 copies of both directions' W_i
-    const void *in16 = nullptr;
-    __nv_bfloat16 *w16 = reinterpret_cast<__nv_bfloat16 *>(ws + p->w_w16);
-    if (p->bf16_gemms && din % 8 == 0 && din >= 128 && (reinterpret_cast<uintptr_t>(w + p->pl[l * p->dirs].w_in) & 15) == 0 &&
-        ((size_t)p->GH * din) % 4 == 0) {
-      if (l > 0) {
-        in16 = rs ? static_cast<const void *>(rs + p->r_y16[l - 1]) : nullptr;
-      } else if (x_bf16) {
-        in16 = x_bf16;
-      } else if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-        CK(to_bf16(x, ws + p->w_x16, (size_t)TB * din, stream));
-        p->launches++;
-        in16 = ws + p->w_x16;
-      }
-      if (in16) {
-        const PseudoLayer &q0 = p->pl[l * p->dirs], &q1 = p->pl[l * p->dirs + p->dirs - 1];
-        const size_t n4 = (size_t)p->GH * din / 4;
-        to_bf16_pair_kernel<<<dim3((unsigned)std::min<size_t>((n4 + 255) / 256, 592), p->dirs), 256, 0, stream>>>(
-            w + q0.w_in, w + q1.w_in, w16, n4);
-        CK(cudaGetLastError());
-        p->launches++;
-      }
-    }
-    a.y16 = nullptr;
-    if (p->bf16_gemms) a.y16 = l == p->layers - 1 ? y_bf16 : (rs ? static_cast<void *>(rs + p->r_y16[l]) : nullptr);
     for (int d = 0; d < p->dirs; d++) {
       const PseudoLayer &q = p->pl[l * p->dirs + d];
       float *gates = rs ? rs + p->r_gates[d][l] : ws + p->w_gates[d];
@@ -444,10 +341,7 @@ b200rnnStatus_t b200rnnForwardEx(b200rnnPlan_t p, int T, const float *x, const v
       g.splits = 1; g.partial = nullptr;
       {
         Timed tm(p, 2, stream);
-        cudaError_t ge = cudaErrorNotSupported;
-        if (in16) ge = gemm_tc_bf16(g, in16, din, w16 + (size_t)d * p->GH * din, din, stream, &p->launches);
-        if (ge == cudaErrorNotSupported) ge = gemm_any(p->math, g, stream, &p->launches);
-        CK(ge);
+        CK(gemm_any(p->math, g, stream, &p->launches));
       }
       a.w_rec[d] = w + q.w_rec;
       a.b_rec[d] = w + q.b_rec;
@@ -521,8 +415,6 @@ b200rnnStatus_t b200rnnBackwardData(b200rnnPlan_t p, int T, const float *y, cons
       a.gates[d] = rs + p->r_gates[d][l];
       a.cell[d] = rs + p->r_cell[d][l];
     }
-    const bool dx16 = p->bf16_gemms && dxl && p->tcNC && !p->tc_no_bwd && din % 8 == 0 && din >= 128 && p->GH % 8 == 0;
-    for (int d = 0; d < p->dirs; d++) a.dg16[d] = dx16 ? static_cast<void *>(rs + p->r_dg16[d][l]) : nullptr;
     {
       Timed tm(p, 1, stream);
       if (p->tcNC && !p->tc_no_bwd) {
@@ -555,14 +447,6 @@ b200rnnStatus_t b200rnnBackwardData(b200rnnPlan_t p, int T, const float *y, cons
     }
     p->launches++;
     if (dxl) {
-      __nv_bfloat16 *wT16 = reinterpret_cast<__nv_bfloat16 *>(ws + p->w_w16);   // [dir][din x GH] = W_i^T in BF16
-      if (dx16) {
-        const PseudoLayer &q0 = p->pl[l * p->dirs], &q1 = p->pl[l * p->dirs + p->dirs - 1];
-        transpose_to_bf16_kernel<<<dim3((din + 31) / 32, (p->GH + 31) / 32, p->dirs), dim3(32, 8), 0, stream>>>(
-            w + q0.w_in, w + q1.w_in, wT16, p->GH, din);
-        CK(cudaGetLastError());
-        p->launches++;
-      }
       for (int d = 0; d < p->dirs; d++) {
         const PseudoLayer &q = p->pl[l * p->dirs + d];
         GemmArgs g = {};
@@ -572,10 +456,7 @@ b200rnnStatus_t b200rnnBackwardData(b200rnnPlan_t p, int T, const float *y, cons
         g.C = dxl; g.ldc = din;
         g.splits = 1;
         Timed tm(p, 2, stream);
-        cudaError_t ge = cudaErrorNotSupported;
-        if (dx16) ge = gemm_tc_bf16(g, rs + p->r_dg16[d][l], p->GH, wT16 + (size_t)d * din * p->GH, p->GH, stream, &p->launches);
-        if (ge == cudaErrorNotSupported) ge = gemm_any(p->math, g, stream, &p->launches);
-        CK(ge);
+        CK(gemm_any(p->math, g, stream, &p->launches));
       }
     }
   }
@@ -607,7 +488,7 @@ b200rnnStatus_t b200rnnBackwardWeights(b200rnnPlan_t p, int T, const float *x, c
       g.C = dw + q.w_in; g.ldc = din;
       g.splits = kSplitK; g.partial = ws + p->w_splitk;
       {
-        Timed tm(p, 2, stream);
+        Timed tm(p, 3, stream);
         CK(gemm_any(p->math, g, stream, &p->launches));
       }
       // dR += dGrec^T . h_prev    h_prev(t) = y(t -+ 1): a row shift of B
@@ -622,14 +503,14 @@ b200rnnStatus_t b200rnnBackwardWeights(b200rnnPlan_t p, int T, const float *x, c
         r.A = dg + sh_g * GH; r.sam = 1; r.sak = GH;
         r.C = dw + q.w_rec;
         {
-          Timed tm(p, 2, stream);
+          Timed tm(p, 3, stream);
           CK(gemm_any(p->math, r, stream, &p->launches));
         }
         if (p->mode == 3) {  // n-gate: recurrent-side gradient lives in the cell buffer
           r.M = H;
           r.A = dq + sh_g * H; r.sam = 1; r.sak = H;
           r.C = dw + q.w_rec + (size_t)2 * H * H;
-          Timed tm(p, 2, stream);
+          Timed tm(p, 3, stream);
           CK(gemm_any(p->math, r, stream, &p->launches));
         }
       }
@@ -752,7 +633,7 @@ b200rnnStatus_t b200rnnSetProfiling(b200rnnPlan_t p, int enable) {
 }
 
 b200rnnStatus_t b200rnnGetProfile(b200rnnPlan_t p, int category, float *total_ms, int *launches) {
-  if (!p || category < 0 || category > 2 || !total_ms || !launches) return B200RNN_STATUS_INVALID_VALUE;
+  if (!p || category < 0 || category > 3 || !total_ms || !launches) return B200RNN_STATUS_INVALID_VALUE;
   float tot = 0.f;
   for (size_t i = 0; i < p->ev_used[category]; i++) {
     float ms = 0.f;

@@ -40,8 +40,6 @@ struct GemmArgs {
   int nb;
   int splits;
   float *partial;
-  void *C16;   // optional BF16 copy of C (tensor-core path, splits == 1): row pitch ldc16 elements
-  int ldc16;
 };
 cudaError_t gemm_fp32(const GemmArgs &g, cudaStream_t stream, int *launches);
 // C = beta*C + bias + sum_z partial[z]  (fixed summation order)
@@ -49,9 +47,6 @@ cudaError_t splitk_reduce(const GemmArgs &g, cudaStream_t stream);
 // tcgen05 kind::tf32 GEMM fed by TMA (rnn_gemm_tc.cu); cudaErrorNotSupported when the
 // operands break TMA's alignment rules (16-byte base, row pitch % 4 floats)
 cudaError_t gemm_tc(const GemmArgs &g, cudaStream_t stream, int *launches);
-// BF16 operands, both K-major: C[M x N] = alpha * A16[M x K] . B16[N x K]^T + beta*C + bias (g.A / g.B are ignored)
-cudaError_t gemm_tc_bf16(const GemmArgs &g, const void *A16, long long lda, const void *B16, long long ldb,
-                         cudaStream_t stream, int *launches);
 // math: 0 = fp32 FMA, 1 = tensor cores with fp32 fallback for unaligned operands
 extern int g_last_gemm_tc;  // 1 if the last gemm_any ran on tcgen05
 cudaError_t gemm_any(int math, const GemmArgs &g, cudaStream_t stream, int *launches);
@@ -85,10 +80,6 @@ struct RecArgs {
   int save;               // fwd: 1 = keep activations/cell for backward
   long long *dbg;         // per-phase cycle counters of cluster 0 / CTA 0; only read by kernels built with
                           // -DB200RNN_PHASE_COUNTERS (tuning builds), ignored by release kernels
-  void *y16;              // fwd (tensor kernels), optional: BF16 copy of y, [T*B x H*dirs] -- the next layer's
-                          // projection GEMM then reads half the bytes and runs kind::f16
-  void *dg16[2];          // bwd (tensor kernels), optional: BF16 copy of the input-side gate gradients [T*B x G*H]
-                          // (the A operand of the dx GEMM)
   float *bias_partial;    // bwd (tensor kernels): [chunk][dir][side 0 = input, 1 = recurrent][G*H] sums of the
                           // gate gradients over time and the chunk's utterances (the bias gradients)
 };

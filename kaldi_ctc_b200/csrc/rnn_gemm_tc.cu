@@ -21,7 +21,6 @@
 // The ticket counter makes the kernel indifferent to how many of its CTAs are resident: the
 // weight-gradient GEMMs run on a side stream next to the persistent recurrent kernels, which pin
 // 80 SMs for milliseconds; CTAs that only become resident later find the queue drained and exit.
-#include <cuda_bf16.h>
 #include <stdio.h>
 
 #include "rnn_common.cuh"
@@ -32,8 +31,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int TBM = 128, TBK32 = 32, TBK = TBK32;  // tf32: 32 elements = one 128-byte swizzle row
-constexpr int TBK16 = 64;           // bf16: 64 elements = one 128-byte swizzle row (same bytes per stage, twice the K)
+constexpr int TBM = 128, TBK = 32;  // tf32: 32 elements = one 128-byte swizzle row
 constexpr int kABytes = TBM * TBK * 4;  // 16 KB
 constexpr int kEpiWarps = 8;            // two per TMEM lane quarter, each takes half of the tile's columns
 constexpr int kThreads = 64 + 32 * kEpiWarps;
@@ -59,18 +57,12 @@ struct TcParams {
   float *partial;
   int tiles_m, tiles_n, total;   // total = tiles_m * tiles_n * splits
   int *ticket;                   // [0] next tile, [1] CTAs finished (both self-resetting)
-  __nv_bfloat16 *C16;            // optional: a BF16 copy of the result (same shape, row pitch ldc16), direct mode only
-  int ldc16;
 };
 
-// BF16 = true: both operands are BF16 in HBM, K-major (kind::f16, K = 16 per instruction); the tile bytes, the
-// swizzle and the descriptor arithmetic are those of the tf32 K-major case, a stage just spans 64 instead of 32 K.
-template <bool A_KMAJOR, bool B_KMAJOR, int TBN, bool BF16 = false>
+template <bool A_KMAJOR, bool B_KMAJOR, int TBN>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
-  static_assert(!BF16 || (A_KMAJOR && B_KMAJOR), "the BF16 variant takes K-major operands");
   using C = Cfg<TBN>;
-  constexpr int TBK = BF16 ? TBK16 : TBK32;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   uint8_t *sA = smem;                           // [kStages][16 KB]
@@ -161,7 +153,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = instr_desc(BF16 ? kFmtBF16 : kFmtTF32, A_KMAJOR ? 0 : 1, B_KMAJOR ? 0 : 1, TBM, TBN);
+    constexpr uint32_t idesc = instr_desc(kFmtTF32, A_KMAJOR ? 0 : 1, B_KMAJOR ? 0 : 1, TBM, TBN);
     uint32_t it = 0, ai = 0;
     for (uint32_t qi = 0;; qi++) {
       mbar_wait(q_full + (qi % kQ), (qi / kQ) & 1);
@@ -183,7 +175,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // warp-uniform issue (descriptors stay in uniform registers), one elected lane issues
         const uint32_t a = smem_u32(sA + s * kABytes), b = smem_u32(sB + s * C::kBBytes);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {   // four MMAs per stage: K = 8 (tf32) or 16 (bf16) each = 32 bytes of a row
+        for (int k = 0; k < TBK / 8; k++) {
           // K-major (SW128, 16 B chunks): 8-row groups are 1024 B apart (SBO); a K step of 8 tf32
           //   is +32 B inside the 128 B swizzle row.
           // MN-major tf32 must use the 32 B-chunk flavour of the 128 B swizzle: atoms of 4 K-rows
@@ -193,10 +185,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                        : smem_desc(a + k * 1024, TBK * 128, 512, kLayoutSw128Base32);
           const uint64_t bd = B_KMAJOR ? smem_desc(b + k * 32, 0, 1024, kLayoutSw128)
                                        : smem_desc(b + k * 1024, TBK * 128, 512, kLayoutSw128Base32);
-          if (elect_one()) {
-            if (BF16) mma_bf16(acc, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else mma_tf32(acc, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          if (elect_one()) mma_tf32(acc, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
         if (elect_one()) {
           tc_commit(empty + s);                      // frees the smem stage when these MMAs retire
@@ -268,11 +257,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               }
               *reinterpret_cast<float4 *>(row + n) = make_float4(v[0], v[1], v[2], v[3]);
-              if (direct && p.C16) {
-                const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
-                *reinterpret_cast<uint2 *>(p.C16 + (size_t)m * p.ldc16 + n) =
-                    make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
-              }
             } else {
 #pragma unroll
               for (int e = 0; e < 4; e++) {
@@ -284,7 +268,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   if (p.bias_b && n + e < p.nb) x += p.bias_b[n + e];
                 }
                 row[n + e] = x;
-                if (direct && p.C16) p.C16[(size_t)m * p.ldc16 + n + e] = __float2bfloat16_rn(x);
               }
             }
           }
@@ -334,17 +317,16 @@ EncodeTiledFn encode_fn() {
 }
 
 // fp32 matrix with `inner` contiguous elements per row, `outer` rows, row pitch ld
-bool make_map(CUtensorMap *map, const void *base, long long inner, long long outer, long long ld,
-              int box_inner, int box_outer, CUtensorMapSwizzle swz, bool bf16 = false) {
+bool make_map(CUtensorMap *map, const float *base, long long inner, long long outer, long long ld,
+              int box_inner, int box_outer, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
-  const int esz = bf16 ? 2 : 4;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * esz) % 16) || inner <= 0 || outer <= 0) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 4) || inner <= 0 || outer <= 0) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * esz};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), gdim, gstr, box, estr,
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
@@ -401,19 +383,19 @@ int sm_count() {
   return n[dev] > 0 ? n[dev] : 148;
 }
 
-template <bool AK, bool BK, int TBN, bool BF16 = false>
+template <bool AK, bool BK, int TBN>
 cudaError_t launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, cudaStream_t s) {
   const size_t smem = Cfg<TBN>::kSmem;
   static bool attr_done[64] = {};   // per device: cudaFuncSetAttribute does not carry over to other GPUs
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<AK, BK, TBN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<AK, BK, TBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   const int grid = p.total < sm_count() ? p.total : sm_count();
-  tc_gemm_kernel<AK, BK, TBN, BF16><<<grid, kThreads, smem, s>>>(ta, tb, p);
+  tc_gemm_kernel<AK, BK, TBN><<<grid, kThreads, smem, s>>>(ta, tb, p);
   return cudaGetLastError();
 }
 
@@ -483,9 +465,6 @@ cudaError_t gemm_tc(const GemmArgs &g, cudaStream_t stream, int *launches) {
   p.total = p.tiles_m * p.tiles_n * splits;
   p.ticket = ticket_slot();
   if (!p.ticket) return cudaErrorMemoryAllocation;
-  p.C16 = splits == 1 ? reinterpret_cast<__nv_bfloat16 *>(g.C16) : nullptr;
-  p.ldc16 = g.ldc16;
-  if (g.C16 && splits != 1) return cudaErrorNotSupported;
   cudaError_t e = tbn == 256 ? launch_any<256>(ak, bk, ta, tb, p, stream) : launch_any<128>(ak, bk, ta, tb, p, stream);
   if (e != cudaSuccess) return e;
   if (launches) (*launches)++;
@@ -495,35 +474,6 @@ cudaError_t gemm_tc(const GemmArgs &g, cudaStream_t stream, int *launches) {
     e = splitk_reduce(r, stream);
     if (launches) (*launches)++;
   }
-  return e;
-}
-
-// BF16 x BF16 -> fp32: A [M x K] and B [N x K] (i.e. C = A . B^T) both K-major BF16 in HBM, row pitches lda / ldb
-// elements (multiples of 8).  Same persistent kernel, tiles and epilogue (bias, beta, optional BF16 copy of C).
-cudaError_t gemm_tc_bf16(const GemmArgs &g, const void *A16, long long lda, const void *B16, long long ldb,
-                         cudaStream_t stream, int *launches) {
-  if (g.M <= 0 || g.N <= 0) return cudaSuccess;
-  if (g.K <= 0) return cudaErrorNotSupported;
-  const int tbn = g.N > 128 ? 256 : 128;
-  CUtensorMap ta, tb;
-  if (!make_map(&ta, A16, g.K, g.M, lda, TBK16, TBM, CU_TENSOR_MAP_SWIZZLE_128B, true) ||
-      !make_map(&tb, B16, g.K, g.N, ldb, TBK16, tbn, CU_TENSOR_MAP_SWIZZLE_128B, true))
-    return cudaErrorNotSupported;
-  TcParams p;
-  p.M = g.M; p.N = g.N; p.K = g.K; p.alpha = g.alpha; p.beta = g.beta;
-  p.C = g.C; p.ldc = g.ldc; p.bias_a = g.bias_a; p.bias_b = g.bias_b; p.nb = g.nb;
-  p.kb_per_split = (g.K + TBK16 - 1) / TBK16;
-  p.splits = 1;
-  p.partial = nullptr;
-  p.tiles_m = (g.M + TBM - 1) / TBM;
-  p.tiles_n = (g.N + tbn - 1) / tbn;
-  p.total = p.tiles_m * p.tiles_n;
-  p.ticket = ticket_slot();
-  if (!p.ticket) return cudaErrorMemoryAllocation;
-  p.C16 = reinterpret_cast<__nv_bfloat16 *>(g.C16);
-  p.ldc16 = g.ldc16;
-  cudaError_t e = tbn == 256 ? launch<true, true, 256, true>(ta, tb, p, stream) : launch<true, true, 128, true>(ta, tb, p, stream);
-  if (e == cudaSuccess && launches) (*launches)++;
   return e;
 }
 

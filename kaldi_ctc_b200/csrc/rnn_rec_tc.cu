@@ -449,9 +449,7 @@ rec_tc_fwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
       const long long c3 = prof ? clock64() : 0;
       long long c4 = c3, c5 = c3, c6 = c3;
       // ---- critical path first: ship h_t to every CTA, then signal
-      const bool send = step + 1 < T;
-      uint4 chs[NJL];   // BF16 chunks (8 consecutive units of one utterance), also what the optional y16 copy stores
-      if (send || a.y16) {
+      if (step + 1 < T) {
         const int pn = (step + 1) & 1;
 #pragma unroll
         for (int j = 0; j < NJL; j++) {
@@ -466,9 +464,7 @@ rec_tc_fwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
           uint4 ch;
           if (lane & 16) ch = make_uint4(lo2, hi2, lo, hi);
           else ch = make_uint4(lo, hi, lo2, hi2);
-          chs[j] = ch;
           const int b = 4 * (jb + j) + s;
-          if (!send) continue;
           if (kSW64) {   // my slice of the tile, in the peers' (64-byte swizzle) layout, into local staging
             if ((lane >> 2) == 0)
               *reinterpret_cast<uint4 *>(hstage + pn * 1024 + b * 64 + ((q ^ ((b >> 1) & 3)) << 4)) = ch;
@@ -478,7 +474,7 @@ rec_tc_fwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
             if (peer_b < NC) st_async_v4(rhs_b + off, ch.x, ch.y, ch.z, ch.w, rhf_b + pn * 8);
           }
         }
-        if (kSW64 && send) {
+        if (kSW64) {
           fence_proxy_async();
           const bool sender = warp == kIssuers && lane < NC;   // lane i ships the slice to CTA i
           // the copy of the previous step has read the other buffer; it (and all older ones) is done before
@@ -511,9 +507,6 @@ rec_tc_fwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
             if (G > 3) gp[3 * H] = sv[j][3];
             if (MODE >= 2) cell[row * H + unit] = sc[j];
           }
-          // BF16 copy of y for the next layer's projection: one 16-byte store per (warp, utterance)
-          if (a.y16 && (lane >> 2) == 0)
-            *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(a.y16) + row * HO + dir * H + crank * UT + q * 8) = chs[j];
         }
       }
       issue_pre(step + kPF);   // refills the slot this step has just consumed
@@ -878,15 +871,6 @@ rec_tc_bwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
           if (G > 1) { gp[H] = dgv[j][1]; gp[2 * H] = dgv[j][2]; }
           if (G > 3) gp[3 * H] = dgv[j][3];
           if (MODE == 3) cell[row * H + unit] = dq[j];
-        }
-        if (a.dg16[dir]) {   // BF16 copy for the dx GEMM: lanes of adjacent units pair up, the even one stores 4 bytes
-          __nv_bfloat16 *g16 = reinterpret_cast<__nv_bfloat16 *>(a.dg16[dir]);
-#pragma unroll
-          for (int g = 0; g < G; g++) {
-            const float other = __shfl_xor_sync(0xffffffffu, dgv[j][g], 4);
-            if (b < nb && !(ul & 1))
-              *reinterpret_cast<uint32_t *>(g16 + ((size_t)t * B + b_lo + b) * GH + (size_t)g * H + unit) = pack_bf16(dgv[j][g], other);
-          }
         }
       }
       if (step + 1 < T) {

@@ -74,22 +74,57 @@ class AffineComponent:
 
 
 class ClipGradientComponent:
-    """nnet2 ClipGradientComponent, norm-based (nnet-cudnn-component.cc:912-957):
-    identity forward; backward scales each derivative row to L2 norm <= threshold.
-    (The optional stochastic self-repair, :980-1055, is off at the recipe's
-    self_repair_scale=1e-5 start-up state: count_ == 0.)"""
+    """nnet2 ClipGradientComponent, norm-based (nnet-cudnn-component.cc:912-1055): identity forward; backward scales
+    each derivative row to L2 norm <= threshold, keeps the component's counters (num_clipped_, count_,
+    num_self_repaired_, num_backpropped_) and adds the stochastic self-repair term (RepairGradients, :970-1055) --
+    all on the device, stream-ordered (b200rnnClipGradientBackprop).  Defaults are InitFromString's (:883-910) except
+    self_repair_scale, which is 0 here (the reference's default of 1.0 is what steps/ctc/nnet2/components.py:60-63
+    leaves in place; pass it explicitly to get the recipe's behaviour)."""
 
-    def __init__(self, dim, clipping_threshold=30.0):
+    def __init__(self, dim, clipping_threshold=30.0, self_repair_clipped_proportion_threshold=0.01,
+                 self_repair_target=0.0, self_repair_scale=0.0, device="cuda:0", seed=0):
         self.dim_, self.clipping_threshold_ = dim, clipping_threshold
-        self.torch = _lib.require_cuda()
+        self.self_repair_clipped_proportion_threshold_ = self_repair_clipped_proportion_threshold
+        self.self_repair_target_, self.self_repair_scale_ = self_repair_target, self_repair_scale
+        self.torch = t = _lib.require_cuda()
+        self.device = t.device(device)
+        # [num_clipped_, count_, num_self_repaired_, num_backpropped_] of THIS component (what the decision reads)
+        self.counters = t.zeros(4, dtype=t.int32, device=self.device)
+        self.ws = None
+        self.rng = np.random.default_rng(seed)   # the reference draws RandUniform() from the C library's rand()
+        self.repair_probability = 0.5            # hard-coded in the reference (:979)
 
     def Propagate(self, inp):
         return inp  # out->CopyFromMat(in): the copy is elided, the values are identical
 
-    def Backprop(self, out_deriv):
-        if self.clipping_threshold_ > 0:
-            rnn.clip_row_norm(self.torch, out_deriv, self.clipping_threshold_)
+    def Backprop(self, out_deriv, in_value=None, to_update=None, force_attempt=None):
+        """in place on out_deriv.  to_update: the ClipGradientComponent whose counters are incremented (the same
+        object when the net updates itself; a copy when training through a gradient Nnet; None: no statistics and
+        no self-repair, as in the reference when to_update is NULL, :960-963)."""
+        if self.clipping_threshold_ <= 0:
+            return out_deriv
+        t = self.torch
+        rows = out_deriv.shape[0]
+        need = rnn.clip_gradient_workspace_bytes(rows)
+        if self.ws is None or self.ws.numel() < need:
+            self.ws = t.empty(int(need * 1.5) + 64, dtype=t.uint8, device=self.device)
+        attempt = False
+        if to_update is not None and self.self_repair_scale_ != 0.0 and in_value is not None:
+            attempt = (self.rng.random() <= self.repair_probability) if force_attempt is None else bool(force_attempt)
+        rnn.clip_gradient_backprop(t, out_deriv, in_value, self.clipping_threshold_,
+                                   self.self_repair_clipped_proportion_threshold_, self.self_repair_target_,
+                                   self.self_repair_scale_, attempt,
+                                   to_update.counters if to_update is not None else None, self.counters, self.ws)
         return out_deriv
+
+    def Info(self):
+        nc, cnt, nsr, nb = [int(v) for v in self.counters.cpu()]
+        return ("ClipGradientComponent, dim=%d, norm-based-clipping=true, clipping-threshold=%g, clipped-proportion=%g, "
+                "num-self-repaired=%d, num-backpropped=%d" % (self.dim_, self.clipping_threshold_, nc / cnt if cnt else 0.0,
+                                                              nsr, nb))
+
+    def ZeroStats(self):
+        self.counters.zero_()
 
 
 class _Grab:
@@ -137,7 +172,7 @@ class NnetCtcUpdater:
     """Mirror of kaldi::ctc::NnetCtcUpdater for the BLSTM/BiGRU + CTC topology."""
 
     def __init__(self, spec, blobs, affine_w, affine_b, minibatch, max_frames, device="cuda:0",
-                 math=rnn.MATH_FP32, world=1, overlap_weights=True, momentum=0.0):
+                 math=rnn.MATH_FP32, world=1, overlap_weights=True, momentum=0.0, self_repair_scale=0.0):
         self.torch = t = _lib.require_cuda()
         self.device = t.device(device)
         self.spec, self.B, self.math, self.world = spec, minibatch, math, world
@@ -152,7 +187,8 @@ class NnetCtcUpdater:
                  "true" if spec.bidir else "false", max_frames, spec.clip_gradient, minibatch))
             c.SetParams(blob)
             self.rnns.append(c)
-            self.clips.append(ClipGradientComponent(spec.H * dirs, spec.clipping_threshold))
+            self.clips.append(ClipGradientComponent(spec.H * dirs, spec.clipping_threshold,
+                                                    self_repair_scale=self_repair_scale, device=device, seed=l))
         self.affine = AffineComponent(affine_w, affine_b, spec.learning_rate, device, math)
         self.ctc = ctc.CtcLoss(device)
         self.max_frames = max_frames
@@ -160,10 +196,6 @@ class NnetCtcUpdater:
         # forward_data_ of the reference: one buffer per component boundary, reused every minibatch
         self.x_dev = t.empty(rows, spec.D, device=self.device)
         self.acts = [t.empty(rows, spec.H * dirs, device=self.device) for _ in blobs]
-        # tensor mode: BF16 copies of the layer outputs, written by the recurrent kernels, read by the next layer's
-        # projection GEMM (b200rnnForwardEx); the fp32 buffers above stay the interface of record
-        self.acts16 = [t.empty(rows, spec.H * dirs, device=self.device, dtype=t.bfloat16) if math == rnn.MATH_TENSOR and
-                       l + 1 < len(blobs) else None for l in range(len(blobs))]
         self.logits = t.empty(rows, spec.A, device=self.device)
         self.deriv = t.empty(rows, spec.A, device=self.device)
         self.dact = [t.empty(rows, spec.H * dirs, device=self.device) for _ in range(2)]
@@ -178,6 +210,8 @@ class NnetCtcUpdater:
         for c in self.rnns:
             c.skip_flag_, c.momentum_ = self.nonfinite_dev, momentum
             c.delta_ = t.zeros_like(c.filter_params_) if momentum != 0.0 else None
+        self.clip_twins = [ClipGradientComponent(c.dim_, c.clipping_threshold_, device=device) for c in self.clips] \
+            if momentum != 0.0 else None
         a = self.affine
         a.skip_flag_, a.momentum_ = self.nonfinite_dev, momentum
         a.delta_ = (t.zeros_like(a.linear_params_), t.zeros_like(a.bias_params_)) if momentum != 0.0 else None
@@ -236,11 +270,9 @@ class NnetCtcUpdater:
 
     def Propagate(self, T):
         rows = T * self.B
-        h, h16 = self.x_dev[:rows], None
-        for c, clip, out, out16 in zip(self.rnns, self.clips, self.acts, self.acts16):
-            o16 = out16[:rows] if out16 is not None else None
-            h = clip.Propagate(c.Propagate(h, out[:rows], inp16=h16, out16=o16))   # (ClipGradient forward = identity)
-            h16 = o16
+        h = self.x_dev[:rows]
+        for c, clip, out in zip(self.rnns, self.clips, self.acts):
+            h = clip.Propagate(c.Propagate(h, out[:rows]))
         return self.affine.Propagate(h, self.logits[:rows])
 
     def ComputeObjfAndDeriv(self, T, flat_labels, label_lengths, input_lengths, sync=True, want_best_pdf=False):
@@ -297,7 +329,10 @@ class NnetCtcUpdater:
             comp_.LaunchDeferredWeights(then_)
 
         for l in range(n - 1, -1, -1):
-            d = self.clips[l].Backprop(d)
+            # (in_value of the clip component = the recurrent layer's output; with momentum the reference updates a
+            #  copy of the net, so the component that decides never sees its own counters move: to_update is a twin)
+            d = self.clips[l].Backprop(d, in_value=self.acts[l][:rows],
+                                       to_update=(self.clips[l] if self.momentum == 0.0 else self.clip_twins[l]) if update else None)
             if pending is not None:
                 release()
                 pending = None
@@ -389,5 +424,5 @@ class NnetCtcUpdater:
         n = 0
         for c in self.rnns:
             n += c.launch_counts.get("fwd", 0) + c.launch_counts.get("bwd_data", 0) + \
-                c.launch_counts.get("bwd_weights", 0) + 1 + 1  # + ClipAndUpdate + ClipRowNorm
+                c.launch_counts.get("bwd_weights", 0) + 1 + 2  # + update + ClipGradient (clip rows, finalize)
         return n + 3 + 4 + 2 + 2   # CTC 3, affine GEMMs 3 (+ split-K reduce), column sums 2, affine updates 2

@@ -37,12 +37,13 @@ def lib():
         L.b200rnnGetWorkspaceSize.argtypes = [vp, ctypes.POINTER(sz)]
         L.b200rnnGetReserveSize.argtypes = [vp, ctypes.POINTER(sz)]
         L.b200rnnForward.argtypes = [vp, i, vp, vp, vp, vp, vp, vp]
-        L.b200rnnForwardEx.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp, vp]
         L.b200rnnBackwardData.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp]
         L.b200rnnBackwardWeights.argtypes = [vp, i, vp, vp, vp, vp, vp, vp]
         L.b200rnnClipAndUpdate.argtypes = [vp, vp, sz, f, f, vp]
         L.b200rnnUpdate.argtypes = [vp, vp, vp, sz, f, f, f, vp, vp]
         L.b200rnnClipRowNorm.argtypes = [vp, i, i, f, vp]
+        L.b200rnnClipGradientWorkspaceSize.argtypes = [i, ctypes.POINTER(sz)]
+        L.b200rnnClipGradientBackprop.argtypes = [vp, vp, i, i, f, f, f, f, i, vp, vp, vp, sz, vp]
         L.b200rnnGemm.argtypes = [i, i, i, i, i, f, vp, i, vp, i, f, vp, i, vp, i, vp, sz, vp]
         L.b200rnnColumnSums.argtypes = [vp, i, i, i, f, vp, i, vp, sz, vp]
         L.b200rnnSetProfiling.argtypes = [vp, i]
@@ -196,9 +197,7 @@ class CuDNNRecurrentComponent:
     def SetParams(self, blob):
         self.filter_params_ = self.torch.as_tensor(np.asarray(blob, dtype=np.float32)).to(self.device).clone()
 
-    def Propagate(self, inp, out=None, inference=False, inp16=None, out16=None):
-        """inp16 / out16 (tensor mode only): optional BF16 copies of inp (from the producing component) and of the
-        output (for the next one), [rows, dim] torch.bfloat16 -- b200rnnForwardEx's side channel."""
+    def Propagate(self, inp, out=None, inference=False):
         torch = self.torch
         if self.mini_batch_ == 0:
             self.InitMiniBatch(1)
@@ -212,16 +211,9 @@ class CuDNNRecurrentComponent:
         # :534: B==1 -> cudnnRNNForwardInference (no reserve space)
         reserve = None if (self.mini_batch_ == 1 or inference) else self.reserve_space_.data_ptr()
         with torch.cuda.device(self.device):
-            if inp16 is not None:
-                assert inp16.dtype == torch.bfloat16 and inp16.is_contiguous() and tuple(inp16.shape) == tuple(inp.shape)
-            if out16 is not None:
-                assert out16.dtype == torch.bfloat16 and out16.is_contiguous() and tuple(out16.shape) == tuple(out.shape)
-            _check(lib().b200rnnForwardEx(self.plan.h, T, inp.data_ptr(),
-                                          inp16.data_ptr() if inp16 is not None else None,
-                                          self.filter_params_.data_ptr(), out.data_ptr(),
-                                          out16.data_ptr() if out16 is not None else None,
-                                          self.work_space_.data_ptr(), reserve,
-                                          _stream(torch, self.device)), "b200rnnForwardEx")
+            _check(lib().b200rnnForward(self.plan.h, T, inp.data_ptr(), self.filter_params_.data_ptr(),
+                                        out.data_ptr(), self.work_space_.data_ptr(), reserve,
+                                        _stream(torch, self.device)), "b200rnnForward")
         self.launch_counts["fwd"] = self.plan.last_launches()
         return out
 
@@ -342,6 +334,25 @@ def update(torch, w, dw, lr, clip, delta=None, momentum=0.0, skip_flag=None):
                                w.numel(), lr, clip, momentum,
                                skip_flag.data_ptr() if skip_flag is not None else None,
                                _stream(torch, w.device)), "b200rnnUpdate")
+
+
+def clip_gradient_workspace_bytes(rows):
+    n = ctypes.c_size_t()
+    _check(lib().b200rnnClipGradientWorkspaceSize(int(rows), ctypes.byref(n)), "b200rnnClipGradientWorkspaceSize")
+    return n.value
+
+
+def clip_gradient_backprop(torch, deriv, in_value, threshold, prop_threshold, target, scale, attempt_repair,
+                           counters, decide_counters, workspace):
+    """b200rnnClipGradientBackprop: ClipGradientComponent::Backprop incl. counters and self-repair, in place."""
+    rows, cols = deriv.shape
+    _check(lib().b200rnnClipGradientBackprop(
+        deriv.data_ptr(), in_value.data_ptr() if in_value is not None else None, rows, cols, threshold,
+        prop_threshold, target, scale, int(bool(attempt_repair)),
+        counters.data_ptr() if counters is not None else None,
+        decide_counters.data_ptr() if decide_counters is not None else None,
+        workspace.data_ptr(), workspace.numel() * workspace.element_size(), _stream(torch, deriv.device)),
+        "b200rnnClipGradientBackprop")
 
 
 def clip_row_norm(torch, d, threshold):

@@ -16,11 +16,13 @@
  * (e.g. `p0 + (p25 - p0) * value * (1/64.0)` is float*float -> double multiply -> double add ->
  * float).  Built with -ffp-contract=off and without FMA, like Kaldi's own build (-msse -msse2).
  *
- * Pinning: the reference holds no golden vectors for this path (matrix-lib-test.cc:4126-4230 only
- * checks properties on random matrices) and kaldi-matrix does not build here (needs BLAS/LAPACK
- * headers), so parity is "unpinned by the reference"; tests/test_feat_oracle.py pins this file with
- * the reference test's own properties (sizes, re-compression stability, row/column access agreeing
- * with CopyToMat) plus hand-computed known answers for both storage formats.
+ * Pinning: PINNED AGAINST THE REFERENCE'S OWN CODE.  oracle/ref/Makefile compiles the reference's
+ * src/matrix/compressed-matrix.cc and src/ctc/ctc-nnet-update.cc where they lie (oracle/_ref/), and
+ * tests/test_reference_linked_cpu.py checks this file against them: decompression (CopyToMat) bit for bit,
+ * compression byte for byte on random and pathological matrices of both storage formats, FormatNnetInput bit
+ * for bit with splicing contexts, left context and speaker vectors.  (The reference holds no golden vectors of
+ * its own for this path: matrix-lib-test.cc:4126-4230 only checks properties on random matrices;
+ * tests/test_feat_oracle.py keeps those properties and hand-computed known answers as a second pin.)
  */
 #include <math.h>
 #include <stdint.h>

@@ -149,6 +149,39 @@ def decodable(nnet_output, prob_scale=1.0, blank_threshold=1.0, priors=None, flo
     return lp * dtype(prob_scale)                   # :83
 
 
+def clip_gradient_backprop(deriv, in_value, threshold, counters, prop_threshold=0.01, target=0.0, scale=1.0,
+                           attempt_repair=False):
+    """ClipGradientComponent::Backprop + RepairGradients (src/nnet2/nnet-cudnn-component.cc:936-1055), restated in
+    numpy (fp64).  counters = [num_clipped, count, num_self_repaired, num_backpropped] of the component (updated in
+    place, the net updating itself); attempt_repair stands for RandUniform() <= repair_probability.
+    Returns the new in_deriv."""
+    d = np.array(deriv, np.float64)
+    nrm2 = (d * d).sum(1) / threshold ** 2
+    clipped = nrm2 > 1.0
+    d[clipped] *= (nrm2[clipped] ** -0.5)[:, None]
+    counters[0] += int(clipped.sum())
+    counters[1] += d.shape[0]
+    counters[3] += 1
+    if not attempt_repair or prop_threshold >= 1.0 or scale == 0.0 or counters[1] == 0:
+        return d
+    prop = counters[0] / counters[1]
+    if prop <= prop_threshold:
+        return d
+    counters[2] += 1
+    v = np.asarray(in_value, np.float64)
+    sign = np.where(v > 0, 1.0, -1.0)
+    repair = np.maximum(np.abs(v) - target, 0.0) * sign
+    dn = np.sqrt((d * d).sum(1))
+    magnitude = scale * prop * dn.mean()
+    rn = np.sqrt((repair * repair).sum(1))
+    s2 = magnitude / rn.mean() if rn.sum() != 0 else 0.0
+    d = d - (s2 / 0.5) * repair
+    dn2 = np.sqrt((d * d).sum(1))
+    if dn2.sum() != 0:
+        d *= dn.sum() / dn2.sum()
+    return d
+
+
 # ---- training input path (oracle/feat_oracle.c) ---------------------------------------------------
 def cm_compress(mat, force_format=0):
     """CompressedMatrix::CopyFromMat -> the in-memory image as bytes (b"" for an empty matrix)."""

@@ -20,8 +20,11 @@
  *   - cuDNN's documented cell equations (gate order LSTM i,f,g,o; GRU r,z,n;
  *     two bias vectors per gate; GRU's recurrent n-bias sits inside r*(...)),
  * and is pinned independently against torch.nn.LSTM/GRU/RNN in fp64
- * (tests/golden/make_golden.py) and by finite differences
- * (tests/test_rnn_oracle.py).
+ * (tests/golden/make_golden.py), by finite differences (tests/test_rnn_oracle.py),
+ * against the same layers written on the reference's own kaldi::Matrix operations
+ * (oracle/ref/kaldi_cpu_path.cc, compiled from /root/reference by oracle/ref/Makefile)
+ * and -- through the product's exact fp32 mode, which matches this file to 1e-6 --
+ * against real cuDNN 9 on the GPU (tests/test_cudnn9_crosscheck_gpu.py).
  *
  * Built twice (oracle/Makefile): REAL=float rnn_oracle_f32 (the reference's
  * arithmetic type, also the timed CPU baseline) and REAL=double

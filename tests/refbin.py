@@ -8,12 +8,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
 HARNESS = os.path.join(REFDIR, "ref_component_harness")
 TRAIN = os.path.join(REFDIR, "ref_ctc_train")
+NNET3 = os.path.join(REFDIR, "ref_nnet3_harness")
 CPULIB = os.path.join(REFDIR, "libkaldi_ref_cpu.so")
 
 
 def ensure_built(target="all"):
     """Returns True when the binaries exist; builds them when the reference tree is present."""
-    want = {"gpu": [HARNESS, TRAIN], "cpu": [CPULIB], "all": [HARNESS, TRAIN, CPULIB]}[target]
+    want = {"gpu": [HARNESS, TRAIN, NNET3], "cpu": [CPULIB], "all": [HARNESS, TRAIN, NNET3, CPULIB]}[target]
     if all(os.path.exists(p) for p in want):
         return True
     if not os.path.isdir("/root/reference/src"):

@@ -7,6 +7,7 @@ kaldi_ctc_b200/libb200cudnn.so as -lcudnn and libb200ctc.so as -lwarpctc:
 
   oracle/_ref/ref_component_harness   integration/kaldi/harness/component_harness.cc on those objects
   oracle/_ref/ref_ctc_train           the reference's training binary itself
+  oracle/_ref/ref_nnet3_harness       the nnet3 adapter (integration/kaldi/nnet3) on the reference's src/nnet3 objects
 
 These tests run the binaries on the GPU and compare what the REFERENCE'S host code computed on top of this
 repo's kernels with the CPU oracle: CuDNNRecurrentComponent::InitFromString -> Propagate -> Backprop
@@ -60,6 +61,38 @@ def test_reference_component_on_the_dropin(tmp_path, mode, bidir, math):
     assert np.abs(dx - dxr).max() < tg * max(1.0, np.abs(dxr).max())
     assert np.abs(w2 - w2r).max() < tg * lr * max(1.0, np.abs(dwr).max()) + 1e-7
     assert np.abs(w2 - w).max() > 1e-4                # the update really happened
+
+
+@pytest.mark.parametrize("mode,bidir,exact", [(2, True, 1), (3, True, 1), (2, False, 1), (2, True, 0)])
+def test_nnet3_adapter_linked_against_reference_nnet3(tmp_path, mode, bidir, exact):
+    """integration/kaldi/nnet3/nnet-b200-recurrent-component.h compiled and LINKED with the reference's src/nnet3
+    objects (nnet-component-itf.cc, nnet-parse.cc, nnet-common.cc, ...), driven through the nnet3 Component surface
+    (src/nnet3/nnet-component-itf.h:116-165): InitFromConfig, ReorderIndexes (the harness hands over n-major
+    indexes), PrecomputeIndexes, Propagate, Backprop with to_update, Write/Read, Vectorize."""
+    D, H, B, T = 24, 64, 4, 12
+    dirs = 2 if bidir else 1
+    rng = np.random.default_rng(9)
+    n = pyoracle.rnn_param_count(mode, bidir, 1, D, H)
+    w = (rng.standard_normal(n) * 0.2).astype(np.float32)
+    x = rng.standard_normal((T * B, D)).astype(np.float32)
+    dy = rng.standard_normal((T * B, H * dirs)).astype(np.float32)
+    for name, arr in (("w", w), ("x", x), ("dy", dy)):
+        arr.tofile(tmp_path / (name + ".f32"))
+    lr, clip = 0.05, 0.7
+    cfg = ("input-dim=%d output-dim=%d learning-rate=%g num-layers=1 rnn-mode=%d bidirectional=%s max-seq-length=16 "
+           "clip-gradient=%g exact-fp32=%d" % (D, H, lr, mode, "true" if bidir else "false", clip, exact))
+    out = refbin.run(refbin.NNET3, cfg, T, B, tmp_path / "w.f32", tmp_path / "x.f32", tmp_path / "dy.f32", tmp_path / "o").stdout
+    assert "B200RecurrentComponent" in out
+    y = np.fromfile(tmp_path / "o.y.f32", np.float32).reshape(T * B, H * dirs)
+    dx = np.fromfile(tmp_path / "o.dx.f32", np.float32).reshape(T * B, D)
+    w2 = np.fromfile(tmp_path / "o.w.f32", np.float32)
+    yr, dxr, dwr = pyoracle.rnn(mode, bidir, 1, H, x, w, B, dy=dy, dtype=np.float64)
+    w2r = w + lr * np.clip(dwr, -clip, clip)
+    ty, tg = (1e-5, 1e-4) if exact else (5e-3, 1e-2)
+    assert np.abs(y - yr).max() < ty
+    assert np.abs(dx - dxr).max() < tg * max(1.0, np.abs(dxr).max())
+    assert np.abs(w2 - w2r).max() < tg * lr * max(1.0, np.abs(dwr).max()) + 1e-7
+    assert np.abs(w2 - w).max() > 1e-4
 
 
 def _write_model_and_egs(tmp_path, spec, n_utts, t_lo, t_hi, l_lo, l_hi, seed):
