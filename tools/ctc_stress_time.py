@@ -1,6 +1,6 @@
 """Times one b200ctc_loss call on BASELINE configs[4] (A=4000, T_b~U{1500..3000}, L_b~U{50..600}) at a given
-batch size, activations drawn on the device; prints ms and algorithmic GB/s.  The path (streaming / three-kernel)
-follows the library's own choice unless B200CTC_STREAM=0/1 is set.  Usage: python tools/ctc_stress_time.py B [iters]"""
+batch size, activations drawn on the device; prints ms and algorithmic GB/s.  B200CTC_LIB=<path> times another build
+of the library (A/B runs of kernel variants).  Usage: python tools/ctc_stress_time.py B [iters]"""
 import json
 import os
 import sys

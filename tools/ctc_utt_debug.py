@@ -1,5 +1,5 @@
-"""Debug aid: runs one CTC call through the streaming path (B200CTC_STREAM=1 must be set by the caller) and compares
-every utterance with the fp64 oracle: cost, max gradient error and where it is.  Usage: python tools/ctc_stream_debug.py cfg"""
+"""Debug aid: runs one CTC call and compares every utterance with the fp64 oracle: cost, max gradient error and where
+it is (frame, symbol).  Usage: python tools/ctc_utt_debug.py <BASELINE config index | ring>"""
 import os
 import sys
 
