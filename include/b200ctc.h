@@ -60,6 +60,12 @@ size_t b200ctc_algorithmic_bytes(const int *label_lengths,
                                  const int *input_lengths, int alphabet_size,
                                  int minibatch);
 
+/* Test / tuning hook, not needed in production: overrides one of the library's internal launch choices for
+ * the rest of the process (the same switches the B200CTC_<KEY> environment variables set at load time:
+ * "RING" -1/0/1, "GROUPS", "P", "NA", "NT", "PROFILE", "ONE_STREAM").  Every setting computes the
+ * same function; the parity tests use it to force each kernel variant.  Returns 0, or -1 for an unknown key. */
+int b200ctc_set_tuning(const char *key, int value);
+
 /* Number of kernels one b200ctc_loss call launches (for bench.py's count). */
 int b200ctc_launches_per_call(int with_gradients);
 

@@ -926,12 +926,13 @@ struct Staging {
   bool pending = false;
 };
 
-// Tuning switches: read from the environment ONCE per process (none is needed in production).
+// Tuning switches: read from the environment ONCE per process (none is needed in production); tests and the
+// tools under tools/ change them in-process through b200ctc_set_tuning().
 struct Tuning {
   int force_p, ring, na, nt, profile, groups, one_stream;
 };
-const Tuning &tuning() {
-  static const Tuning t = [] {
+Tuning &tuning() {
+  static Tuning t = [] {
     auto geti = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
     Tuning v;
     v.force_p = geti("B200CTC_P", 0);
@@ -944,6 +945,15 @@ const Tuning &tuning() {
     return v;
   }();
   return t;
+}
+int *tuning_field(const char *key) {
+  Tuning &t = tuning();
+  struct { const char *k; int *v; } tab[] = {
+      {"P", &t.force_p}, {"RING", &t.ring}, {"NA", &t.na}, {"NT", &t.nt}, {"PROFILE", &t.profile},
+      {"GROUPS", &t.groups}, {"ONE_STREAM", &t.one_stream}};
+  for (auto &e : tab)
+    if (key && strcmp(key, e.k) == 0) return e.v;
+  return nullptr;
 }
 
 // Everything that belongs to ONE device: function attributes (cudaFuncSetAttribute is per device), the
@@ -1022,7 +1032,7 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   DeviceState *ds = device_state();
   if (!ds) return CTC_STATUS_EXECUTION_FAILED;
   Staging &g_stage = ds->stage;
-  const Tuning &tune = tuning();
+  const Tuning tune = tuning();
   if (!ensure_pinned(g_stage, p.header_bytes, (size_t)B)) return CTC_STATUS_MEMOPS_FAILED;
   unsigned char *h = g_stage.pinned;
   UttMeta *hm = reinterpret_cast<UttMeta *>(h + p.off_meta);
@@ -1393,6 +1403,14 @@ size_t b200ctc_algorithmic_bytes(const int *label_lengths, const int *input_leng
   }
   return 4 * (size_t)alphabet_size * sumT + 4 * (size_t)alphabet_size * Tmax * minibatch +
          4 * sumL + 4 * (size_t)minibatch;
+}
+
+int b200ctc_set_tuning(const char *key, int value) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  int *f = tuning_field(key);
+  if (!f) return -1;
+  *f = value;
+  return 0;
 }
 
 int b200ctc_launches_per_call(int with_gradients) { return with_gradients ? 3 : 2; }

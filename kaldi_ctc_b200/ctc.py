@@ -82,6 +82,15 @@ def workspace_size(label_lengths, input_lengths, alphabet_size):
     return n.value
 
 
+def set_tuning(key, value):
+    """Test / tuning hook (include/b200ctc.h b200ctc_set_tuning): forces one of the library's launch choices
+    ("RING", "GROUPS", "P", ...) for the rest of the process; -1 / 0 restore the default of most keys."""
+    L = lib()
+    L.b200ctc_set_tuning.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    if L.b200ctc_set_tuning(key.encode(), int(value)) != 0:
+        raise KeyError(key)
+
+
 def algorithmic_bytes(label_lengths, input_lengths, alphabet_size):
     ll, il = _i32(label_lengths), _i32(input_lengths)
     return lib().b200ctc_algorithmic_bytes(_ptr(ll), _ptr(il), int(alphabet_size), len(ll))

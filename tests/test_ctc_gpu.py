@@ -72,14 +72,16 @@ def test_wide_alphabet_slice_of_config5(ctx):
 
 
 @pytest.mark.parametrize("A,groups", [(4000, 1), (4000, 3), (1028, 2)])
-def test_wide_alphabet_ring_kernel(ctx, monkeypatch, A, groups):
+def test_wide_alphabet_ring_kernel(ctx, A, groups):
     """The persistent TMA-ring gradient kernel (normally chosen for slabs >= 64 MB), forced on a small
     ragged batch: an empty label string, P=1 and P=2 lattices in one call is not possible (P is per call),
     so L up to 300 gives P=2; one infeasible utterance (zero row block), padded frames, several utterance
     groups on side streams."""
     from oracle import pyoracle
-    monkeypatch.setenv("B200CTC_RING", "1")
-    monkeypatch.setenv("B200CTC_GROUPS", str(groups))
+    ctc = ctx[1]
+    # (b200ctc_set_tuning, not the environment: the library reads B200CTC_* once per process)
+    ctc.set_tuning("RING", 1)
+    ctc.set_tuning("GROUPS", groups)
     rng = np.random.default_rng(A + groups)
     il = np.array([90, 400, 37, 333, 20, 256, 1], np.int32)
     ll = np.array([0, 300, 12, 150, 30, 100, 1], np.int32)   # utterance 4: L=30 > T=20 -> infeasible
@@ -89,7 +91,12 @@ def test_wide_alphabet_ring_kernel(ctx, monkeypatch, A, groups):
         act[il[b]:, b, :] = 0
     fl = np.concatenate([rng.integers(1, A, size=int(l)) for l in ll]).astype(np.int32)
     c_ref, g_ref = pyoracle.ctc(act, fl, ll, il, dtype=np.float64)
-    costs, grad = _run(ctx, act, fl, ll, il)
+    try:
+        costs, grad = _run(ctx, act, fl, ll, il)
+    except Exception:
+        ctc.set_tuning("RING", -1)
+        ctc.set_tuning("GROUPS", 0)
+        raise
     feas = np.array([0, 1, 2, 3, 5, 6])
     np.testing.assert_allclose(costs[feas], c_ref[feas], rtol=LOSS_RTOL)
     assert np.abs(grad[:, feas] - g_ref[:, feas]).max() < GRAD_ATOL
@@ -97,8 +104,12 @@ def test_wide_alphabet_ring_kernel(ctx, monkeypatch, A, groups):
     for b in range(B):
         assert np.abs(grad[il[b]:, b]).max(initial=0) == 0
     # and it is the same function as the row-per-warp kernel
-    monkeypatch.setenv("B200CTC_RING", "0")
-    costs2, grad2 = _run(ctx, act, fl, ll, il)
+    try:
+        ctc.set_tuning("RING", 0)
+        costs2, grad2 = _run(ctx, act, fl, ll, il)
+    finally:
+        ctc.set_tuning("RING", -1)
+        ctc.set_tuning("GROUPS", 0)
     np.testing.assert_array_equal(costs, costs2)
     assert np.abs(grad - grad2).max() < 1e-6
 
