@@ -261,112 +261,137 @@ ctc_rowstats_gather_kernel(CtcDev d) {
 //   X_i <- El_i + lse(X_i, Y_i, skip_i ? X_{i-1} : 0)
 // alpha: Y_i = state 2i, X_i = state 2i+1, time ascending, label i.
 // beta : Y_i = state 2(L-i), X_i = state 2(L-i)-1, time descending, label L-1-i.
-// The per-frame loop is ISSUE-bound as much as latency-bound (a first version spent ~225 SASS
-// instructions per frame on index arithmetic: step / F, step % 8, role selects, 64-bit address
-// rebuilds), so the role is a template parameter and every index advances incrementally.
-template <int P, int ROLE>
+// The per-frame loop is bound by instruction issue and by the special-function unit (16 ex2/lg2 per clock and
+// SM), not by latency: one CTA's 20 warps already keep an SM busy.  So the loop is written for instruction
+// count: the role and "every pair of this warp exists" (FULL) are template parameters, every address advances
+// incrementally, the three-term sum of the label state is nested on the two-term sum of the blank state
+// (4 instead of 5 special-function operations per pair), and the end-of-block work (publish the offset,
+// re-centre) sits BETWEEN runs of frames instead of being tested in every frame: an iteration is
+// "exchange the previous frame's boundary state, then compute this frame".
+// log2(2^a + 2^b) with 2 special-function operations and no sorting
+__device__ __forceinline__ float lse2_pair(float a, float b) {
+  return fmaxf(a, b) + lg2_approx(1.0f + ex2_approx(-fabsf(a - b)));
+}
+
+template <int P, int ROLE, bool FULL>
 __device__ __forceinline__ void ctc_ab_run(const CtcDev &d, const UttMeta &um, int b, int r, int nthreads_needed,
-                                           int nbar, uint64_t *my_bar, float *my_stage, float2 *bnd, float *fin,
-                                           int F) {
+                                           int nbar, uint64_t *my_bar, float *my_stage, int stage_floats,
+                                           float2 *bnd, float *fin, int F) {
   const int lane = r & 31, w = r >> 5;
   const int L = um.L, T = um.T, pitch = um.pitch;
   const float *Eg = d.E + um.e_off;
   const int nchunks = (T + F - 1) / F;
+  const bool multi = nbar > 32;   // several warps per direction: the warp-boundary state goes through shared memory
 
   // chunk k (in visiting order) -> first frame and frame count
   auto chunk_lo = [&](int k) { return ROLE ? max(0, T - (k + 1) * F) : k * F; };
   auto chunk_n = [&](int k) { return min(F, T - k * F); };
-  auto issue = [&](int k) {
-    const int st = k % kStages;
+  auto issue = [&](int k, int st) {
     const uint32_t bytes = (uint32_t)chunk_n(k) * pitch * 4u;
     mbar_expect_tx(my_bar + st, bytes);
-    tma_load_1d(my_stage + st * kStageFloats, Eg + (long long)chunk_lo(k) * pitch, bytes, my_bar + st);
+    tma_load_1d(my_stage + st * stage_floats, Eg + (long long)chunk_lo(k) * pitch, bytes, my_bar + st);
   };
   if (r == 0)
-    for (int k = 0; k < min(kStages, nchunks); k++) issue(k);
+    for (int k = 0; k < min(kStages, nchunks); k++) issue(k, k);
 
-  // per-thread lattice slice
+  // per-thread lattice slice: pairs i0 .. i0+P-1, adjacent in E (labels) and in a stored frame
   const int i0 = r * P;
   const int *lab = d.labels + um.lab_off;
   float X[P], Y[P];
-  int eidx[P];      // index of El_i inside a frame of E
-  int soff[P];      // float offset of this pair inside a stored frame
   bool skip[P], hasX[P], hasY[P];
 #pragma unroll
   for (int p = 0; p < P; p++) {
     const int i = i0 + p;
-    hasY[p] = i <= L;
-    hasX[p] = i < L;
+    hasY[p] = FULL || i <= L;
+    hasX[p] = FULL || i < L;
     int li = 0, lprev = -1;
     if (hasX[p]) {
       li = ROLE ? lab[L - 1 - i] : lab[i];
       if (i >= 1) lprev = ROLE ? lab[L - i] : lab[i - 1];
     }
     skip[p] = hasX[p] && i >= 1 && li != lprev;
-    eidx[p] = hasX[p] ? (ROLE ? L - i : 1 + i) : 0;
-    soff[p] = hasY[p] ? (ROLE ? 2 * (L - i) : 2 * i) : 0;
     X[p] = kNeg;
     Y[p] = (i == 0) ? 0.f : kNeg;  // virtual frame "-1": all mass on the first blank
   }
+  constexpr int kDir = ROLE ? -1 : 1;                 // direction of the pair index in memory
+  const int lab0 = ROLE ? L - i0 : 1 + i0;            // index of El_{i0} inside a frame of E (pair p: lab0 + kDir*p)
   // Values are kept relative to a per-thread integer offset c (a float holding an
   // integer): true log2 value = stored + c.  A thread whose states are all still
   // unreachable simply adopts its neighbour's offset.
   float xin = kNeg;  // X_{i0-1} of the previous frame, already relative to c
   float c = 0.f;
-  bool live = (r == 0);
+  bool adopt = false;
 
   const int pitch2 = 2 * pitch;
-  float *o = (ROLE ? d.beta : d.alpha) + um.ab_off + (ROLE ? (long long)(T - 1) * pitch2 : 0);
+  float *o = (ROLE ? d.beta : d.alpha) + um.ab_off + (ROLE ? (long long)(T - 1) * pitch2 : 0) +
+             (ROLE ? 2 * (L - i0) : 2 * i0);          // pair p of this frame: o[2*kDir*p], o[2*kDir*p + 1]
   float *off_out = (ROLE ? d.offB : d.offA) + um.off_off + r;
   const int o_step = ROLE ? -pitch2 : pitch2, e_step = ROLE ? -pitch : pitch;
   const bool writes_off = r < nthreads_needed;
   const int off_stride = (nthreads_needed + 3) & ~3;
-  float2 *bn_w = bnd + w;          // this warp's slot; the double buffer toggles by +-32
-  int par = 0, rn = kRenorm, st = 0;
+  const uint32_t bn_mine = smem_u32(bnd + w);         // this warp's boundary slot; the double buffer toggles by 256 B
+  const bool sends = multi && lane == 31, receives = multi && lane == 0 && w > 0, first = r == 0;
+  uint32_t par = 0;
+  int st = 0, done = 0;
   uint32_t ph = 0;
+  const int R = min(F, kRenorm);                      // frames per run (F is a power of two: runs tile the blocks)
 
   for (int k = 0; k < nchunks; k++) {
     const int n = min(F, T - k * F);
     mbar_wait(my_bar + st, ph);
-    const float *e = my_stage + st * kStageFloats + (ROLE ? (n - 1) * pitch : 0);
-    const bool last_chunk = k == nchunks - 1;
-    for (int f = 0; f < n; f++) {
-      const float Eb = e[0];
-      float El[P];
-#pragma unroll
-      for (int p = 0; p < P; p++) El[p] = hasX[p] ? e[eidx[p]] : kNeg;  // kNeg keeps a missing X at "log 0"
-      e += e_step;
+    const float *e = my_stage + st * stage_floats + (ROLE ? (n - 1) * pitch : 0);
+    for (int f0 = 0; f0 < n; f0 += R) {
+      const int m = min(R, n - f0);
+      for (int j = 0; j < m; j++) {
+        // ---- hand (X_last, c) of the previous frame to the next thread
+        float xv = __shfl_up_sync(0xffffffffu, X[P - 1], 1);
+        float cv = __shfl_up_sync(0xffffffffu, c, 1);
+        if (multi) {
+          if (sends)
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bn_mine + par), "f"(X[P - 1]), "f"(c) : "memory");
+          named_bar_sync(1 + ROLE, nbar);
+          if (receives)
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(xv), "=f"(cv) : "r"(bn_mine + par - 8) : "memory");
+          par ^= 256u;
+        }
+        if (first) {
+          xv = kNeg;
+          cv = c;
+        }
+        if (adopt) c = cv;                   // nothing reachable here at the last block end: follow the neighbour
+        adopt = false;
+        xin = fmaxf(xv + (cv - c), kNeg);    // cv - c is an exact integer
 
-      float nX[P], nY[P];
+        // ---- this frame
+        const float Eb = e[0];
+        float El[P];
 #pragma unroll
-      for (int p = 0; p < P; p++) {
-        const float xp = p == 0 ? xin : X[p - 1];
-        nY[p] = Eb + lse2_2(Y[p], xp);
-        nX[p] = El[p] + lse2_3(X[p], Y[p], skip[p] ? xp : kNeg);
+        for (int p = 0; p < P; p++) El[p] = hasX[p] ? e[lab0 + kDir * p] : kNeg;  // kNeg keeps a missing X at "log 0"
+        e += e_step;
+        float xp = xin;
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+          const float l1 = lse2_pair(Y[p], xp);            // blank state: Y_i, X_{i-1}
+          const float xo = X[p];
+          X[p] = El[p] + lse2_pair(xo, skip[p] ? l1 : Y[p]);   // label state: X_i, Y_i (, X_{i-1})
+          Y[p] = Eb + l1;
+          xp = xo;
+          if (hasY[p])
+            *reinterpret_cast<float2 *>(o + 2 * kDir * p) = ROLE ? make_float2(X[p], Y[p]) : make_float2(Y[p], X[p]);
+        }
+        o += o_step;
       }
-#pragma unroll
-      for (int p = 0; p < P; p++) {
-        Y[p] = nY[p];
-        X[p] = nX[p];
-      }
-      // store this frame (relative to c)
-#pragma unroll
-      for (int p = 0; p < P; p++)
-        if (hasY[p])
-          *reinterpret_cast<float2 *>(o + soff[p]) = ROLE ? make_float2(X[p], Y[p]) : make_float2(Y[p], X[p]);
-      o += o_step;
-      // end of a frame block: publish the offset the block was stored with, re-centre.  c only changes
-      // here: re-centred if the thread has reachable states, otherwise adopted from the left neighbour.
-      const bool block_end = (--rn == 0) || (last_chunk && f == n - 1);
-      if (block_end) {
-        rn = kRenorm;
+      done += m;
+      // ---- end of a frame block: publish the offset the block was stored with, re-centre.  c only changes
+      //      here (re-centred if the thread has reachable states) or, for a thread with nothing reachable, at
+      //      the next exchange (adopted from the left neighbour).
+      if ((done & (kRenorm - 1)) == 0 || done == T) {
         if (writes_off) *off_out = c;
         off_out += off_stride;
         float mx = kNeg;
 #pragma unroll
         for (int p = 0; p < P; p++) mx = fmaxf(mx, fmaxf(hasX[p] ? X[p] : kNeg, hasY[p] ? Y[p] : kNeg));
-        live = mx > -1.0e29f;
-        if (live) {
+        if (mx > -1.0e29f) {
           const float sh = floorf(mx);
 #pragma unroll
           for (int p = 0; p < P; p++) {
@@ -374,25 +399,17 @@ __device__ __forceinline__ void ctc_ab_run(const CtcDev &d, const UttMeta &um, i
             Y[p] = fmaxf(Y[p] - sh, kNeg);
           }
           c += sh;
+        } else {
+          adopt = true;
         }
       }
-      // hand (X_last, c) to the next thread for the next frame
-      const float xs = __shfl_up_sync(0xffffffffu, X[P - 1], 1);
-      const float cs = __shfl_up_sync(0xffffffffu, c, 1);
-      if (lane == 31) bn_w[par] = make_float2(X[P - 1], c);
-      named_bar_sync(1 + ROLE, nbar);
-      float xv = xs, cv = cs;
-      if (lane == 0) {
-        const float2 v = w == 0 ? make_float2(kNeg, c) : bn_w[par - 1];
-        xv = v.x;
-        cv = v.y;
-      }
-      par ^= 32;
-      if (block_end && !live) c = cv;    // nothing reachable here yet: follow the neighbour
-      xin = fmaxf(xv + (cv - c), kNeg);  // cv - c is an exact integer
     }
-    // stage fully consumed (every thread is past the barrier of its last frame) -> refill it
-    if (r == 0 && k + kStages < nchunks) issue(k + kStages);
+    // stage fully consumed -> refill it.  Thread 0 is past the exchange barrier of the chunk's LAST frame, which
+    // every thread reaches only after reading the frame before it; the last frame's own reads are ordered by the
+    // barrier below (one per chunk, several warps only).
+    if (multi) named_bar_sync(1 + ROLE, nbar);
+    else __syncwarp();
+    if (r == 0 && k + kStages < nchunks) issue(k + kStages, st);
     if (++st == kStages) {
       st = 0;
       ph ^= 1;
@@ -432,12 +449,12 @@ __device__ __forceinline__ void ctc_ab_run(const CtcDev &d, const UttMeta &um, i
 }
 
 template <int P>
-__global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int frames_per_stage) {
+__global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int frames_per_stage, int stage_floats) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);               // [2][kStages]
   float2 *bnd = reinterpret_cast<float2 *>(smem_raw + 64);               // [2][2][32] (value, offset)
   float *fin = reinterpret_cast<float *>(smem_raw + 64 + 1024);          // [2][4]
-  float *stages = reinterpret_cast<float *>(smem_raw + 2048);            // [2][kStages][kStageFloats]
+  float *stages = reinterpret_cast<float *>(smem_raw + 2048);            // [2][kStages][stage_floats]
 
   const int b = d.b_lo + blockIdx.x;
   const UttMeta um = d.meta[b];
@@ -456,11 +473,19 @@ __global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int f
   const int nwarps_active = (nthreads_needed + 31) >> 5;
   if ((r >> 5) >= nwarps_active) return;  // idle warps leave; named barriers count the rest
   const int nbar = nwarps_active * 32;
-  if (role == 0)
-    ctc_ab_run<P, 0>(d, um, b, r, nthreads_needed, nbar, mbar, stages, bnd, fin, frames_per_stage);
-  else
-    ctc_ab_run<P, 1>(d, um, b, r, nthreads_needed, nbar, mbar + kStages, stages + kStages * kStageFloats,
-                     bnd + 64, fin + 4, frames_per_stage);
+  // FULL: every pair of every lane of this warp lies inside the lattice and has a label state (i < L)
+  const bool full = ((r >> 5) + 1) * 32 * P <= um.L;
+  uint64_t *bar = mbar + role * kStages;
+  float *stg = stages + (size_t)role * kStages * stage_floats;
+  float2 *bn = bnd + role * 64;
+  float *fn = fin + role * 4;
+  if (role == 0) {
+    if (full) ctc_ab_run<P, 0, true>(d, um, b, r, nthreads_needed, nbar, bar, stg, stage_floats, bn, fn, frames_per_stage);
+    else ctc_ab_run<P, 0, false>(d, um, b, r, nthreads_needed, nbar, bar, stg, stage_floats, bn, fn, frames_per_stage);
+  } else {
+    if (full) ctc_ab_run<P, 1, true>(d, um, b, r, nthreads_needed, nbar, bar, stg, stage_floats, bn, fn, frames_per_stage);
+    else ctc_ab_run<P, 1, false>(d, um, b, r, nthreads_needed, nbar, bar, stg, stage_floats, bn, fn, frames_per_stage);
+  }
 }
 
 // ===========================================================================
@@ -962,7 +987,7 @@ int *tuning_field(const char *key) {
 constexpr int kMaxGroups = 8;
 struct DeviceState {
   int num_sms = 0;
-  bool k2_attr[3] = {false, false, false};   // P = 1, 2, 4
+  size_t k2_smem[3] = {0, 0, 0};   // P = 1, 2, 4: dynamic shared memory already granted to the kernel
   size_t smem3_set = 0, ring_set = 0;
   cudaStream_t hp[kMaxGroups] = {};
   cudaEvent_t e1[kMaxGroups] = {}, e2[kMaxGroups] = {};
@@ -1001,16 +1026,16 @@ bool ensure_pinned(Staging &s, size_t bytes, size_t ncosts) {
 }
 
 template <int P>
-cudaError_t launch_k2(const CtcDev &dev, int B, int NT, int F, cudaStream_t stream, DeviceState *ds) {
-  const size_t smem = 2048 + sizeof(float) * 2 * kStages * kStageFloats;
-  bool &attr_done = ds->k2_attr[P == 1 ? 0 : (P == 2 ? 1 : 2)];
-  if (!attr_done) {
+cudaError_t launch_k2(const CtcDev &dev, int B, int NT, int F, int stage_floats, cudaStream_t stream, DeviceState *ds) {
+  const size_t smem = 2048 + sizeof(float) * 2 * kStages * (size_t)stage_floats;
+  size_t &granted = ds->k2_smem[P == 1 ? 0 : (P == 2 ? 1 : 2)];
+  if (smem > granted) {
     cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_kernel<P>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    granted = smem;
   }
-  ctc_alpha_beta_kernel<P><<<dev.nb, 2 * NT, smem, stream>>>(dev, F);
+  ctc_alpha_beta_kernel<P><<<dev.nb, 2 * NT, smem, stream>>>(dev, F, stage_floats);
   return cudaGetLastError();
 }
 
@@ -1150,7 +1175,11 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   // Launch K1 -> K2 -> K3 per utterance group.  With two groups on two streams the latency-bound
   // alpha/beta recursion of one group runs under the bandwidth-bound row kernels of the other.
   const int NT = (int)align_up((size_t)(npairs + P - 1) / P, 32);
-  const int F = std::max(1, std::min(32, kStageFloats / p.pitch_max));
+  // emission stages of K2: 8 frames each when that fits (a stage then holds one re-centring block), a power of
+  // two in any case; 2 directions x kStages stages, at most ~192 KB of shared memory (one CTA per SM anyway)
+  const int stage_floats = std::min(std::max(kStageFloats, kRenorm * p.pitch_max), 6144);
+  int F = 1;
+  while (F < 32 && 2 * F * p.pitch_max <= stage_floats) F *= 2;
   const int smem_pitch = p.pitch_max;  // gammas of the label states of one row
   const size_t smem3 = sizeof(float) * (size_t)kK3Warps * smem_pitch;
   if (grad) {
@@ -1253,9 +1282,9 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
     set_group(gi);
     cudaStream_t st = ngroups > 1 ? hp[gi] : stream;
     if (ngroups > 1) cudaStreamWaitEvent(st, e1[gi], 0);
-    cudaError_t ce = P == 1   ? launch_k2<1>(dev, B, NT, F, st, ds)
-                     : P == 2 ? launch_k2<2>(dev, B, NT, F, st, ds)
-                              : launch_k2<4>(dev, B, NT, F, st, ds);
+    cudaError_t ce = P == 1   ? launch_k2<1>(dev, B, NT, F, stage_floats, st, ds)
+                     : P == 2 ? launch_k2<2>(dev, B, NT, F, stage_floats, st, ds)
+                              : launch_k2<4>(dev, B, NT, F, stage_floats, st, ds);
     if (ce != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
     if (timeline) cudaEventRecord(tl[gi][2], st);
     if (ngroups > 1) cudaEventRecord(e2[gi], st);
