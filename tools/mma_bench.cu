@@ -95,6 +95,68 @@ void runmw(long long *d) {
   }
 }
 
+
+// Same burst with every MMA operand provably warp-uniform for ptxas: the issuing warp is a template parameter
+// (one code copy per warp), the TMEM base is assumed to be 0 (checked by the caller), the shared-memory address
+// comes from the extern array's shared-window offset, and ONE elect per burst guards the MMAs -- so that the
+// descriptors live in uniform registers and no R2UR / ELECT / VOTEU sits between two UTCHMMA.
+template <int NW, int W>
+__device__ __forceinline__ void burst_uniform(uint32_t b0, int nmma, uint64_t *bar) {
+  constexpr uint32_t idesc = instr_desc(kFmtBF16, 0, 0, 128, 16);
+  const uint64_t bd0 = smem_desc(b0, 0, 1024, kLayoutSw128);
+  if (elect_one()) {
+#pragma unroll
+    for (int i = 0; i < 24 / NW; i++) {
+      const int kk = NW * i + W;
+      if (kk < nmma) mma_bf16_ts(W * 16, 256 + (kk % 20) * 8, bd0 + (uint64_t)(((kk & 3) * 32) >> 4), idesc, i ? 1u : 0u);
+    }
+    tc_commit(bar);
+  }
+  __syncwarp();
+}
+template <int NW>
+__global__ void __launch_bounds__(128, 1) kmu(long long *out, int nmma, int reps) {
+  extern __shared__ __align__(1024) uint8_t smem_al[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t *>(smem_al)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar, NW); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+  asm volatile("fence.proxy.async;" ::: "memory");
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tm = slot;
+  if (threadIdx.x == 0) out[1] = tm;   // must be 0 for this variant
+  const uint32_t b0 = ((smem_u32(smem_al) + 1023u) & ~1023u) + 32768;
+  if (warp < NW && tm == 0) {
+    long long tot = 0;
+    for (int r = 0; r < reps; r++) {
+      asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+      const long long t0 = clock64();
+      if (warp == 0) burst_uniform<NW, 0>(b0, nmma, &bar);
+      else if (warp == 1) burst_uniform<NW, 1 % NW>(b0, nmma, &bar);
+      else if (warp == 2) burst_uniform<NW, 2 % NW>(b0, nmma, &bar);
+      else burst_uniform<NW, 3 % NW>(b0, nmma, &bar);
+      mbar_wait(&bar, r & 1);
+      tot += clock64() - t0;
+    }
+    if (threadIdx.x == 0) out[0] = tot / reps;
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tm, 512); }
+}
+template <int NW>
+void runmu(long long *d) {
+  cudaFuncSetAttribute(kmu<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 70000);
+  for (int nm : {20, 24}) {
+    kmu<NW><<<1, 128, 70000>>>(d, nm, 50);
+    long long h[2] = {0, 0};
+    cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    printf("TS N=16 uniform operands, %d issuing warps, nmma=%2d: cycles=%lld (tmem base %lld)  %s\n", NW, nm, h[0], h[1],
+           cudaGetErrorString(e));
+  }
+}
+
 template <int N, bool TS, int NACC>
 void run(const char *name, long long *d) {
   cudaFuncSetAttribute(k<N, TS, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 70000);
@@ -112,6 +174,9 @@ int main() {
   runmw<1>(d);
   runmw<2>(d);
   runmw<4>(d);
+  runmu<1>(d);
+  runmu<2>(d);
+  runmu<4>(d);
   run<16, false, 1>("SS 1acc", d);
   run<16, true, 1>("TS 1acc", d);
   run<16, true, 4>("TS 4acc", d);
