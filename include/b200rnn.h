@@ -163,6 +163,13 @@ b200rnnStatus_t b200rnnGemm(int transA, int transB, int M, int N, int K, float a
 /* 1 if the most recent GEMM issued by this library ran on tcgen05 (MATH_TENSOR with
  * TMA-compatible operands), 0 if it took the fp32 FMA path. */
 int b200rnnLastGemmUsedTensorCores(void);
+/* 1 if that GEMM was the CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles on the two SMs of a TPC). */
+int b200rnnLastGemmUsedCtaPair(void);
+/* Test / tuning hook, not needed in production: "GEMM_PAIR" = -1 (default: CTA pairs for M >= 2048, N > 128,
+ * no split-K), 0 (never), 1 (whenever the tile shape allows); "GEMM_TMA_STORE" = 1 (default: the CTA-pair kernel
+ * writes its output with TMA tile stores when beta = 0) or 0 (register stores).  Every setting computes the same function.
+ * Returns 0, or -1 for an unknown key. */
+int b200rnnSetTuning(const char *key, int value);
 
 /* Column sums: out[c] = (accumulate ? out[c] : 0) + alpha * sum_r a[r, c]
  * (AffineComponent bias update: bias += lr * colsum(deriv)).  Deterministic. */

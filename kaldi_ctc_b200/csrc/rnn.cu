@@ -3,6 +3,7 @@
 // of forward / backward-data / backward-weights.  Replaces what
 // CuDNNRecurrentComponent gets from cuDNN 5 (src/nnet2/nnet-cudnn-component.cc
 // :100-315 descriptors, :534-555 forward, :576-599 backward).
+#include <string.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -649,6 +650,20 @@ b200rnnStatus_t b200rnnGetProfile(b200rnnPlan_t p, int category, float *total_ms
 }
 
 int b200rnnLastGemmUsedTensorCores(void) { return g_last_gemm_tc; }
+
+int b200rnnLastGemmUsedCtaPair(void) { return g_last_gemm_pair; }
+
+int b200rnnSetTuning(const char *key, int value) {
+  if (key && strcmp(key, "GEMM_PAIR") == 0) {
+    g_gemm_pair = value;
+    return 0;
+  }
+  if (key && strcmp(key, "GEMM_TMA_STORE") == 0) {
+    g_gemm_tma_store = value;
+    return 0;
+  }
+  return -1;
+}
 
 int b200rnnLastLaunchCount(b200rnnPlan_t p) { return p ? p->launches : 0; }
 

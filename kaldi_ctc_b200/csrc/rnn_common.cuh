@@ -49,6 +49,9 @@ cudaError_t splitk_reduce(const GemmArgs &g, cudaStream_t stream);
 cudaError_t gemm_tc(const GemmArgs &g, cudaStream_t stream, int *launches);
 // math: 0 = fp32 FMA, 1 = tensor cores with fp32 fallback for unaligned operands
 extern int g_last_gemm_tc;  // 1 if the last gemm_any ran on tcgen05
+extern int g_gemm_pair;     // CTA-pair (cta_group::2) GEMM kernel: -1 = when the shape qualifies, 0 = never, 1 = whenever possible
+extern int g_gemm_tma_store; // CTA-pair kernel: epilogue through TMA tile stores when beta = 0 (1) or always through registers (0)
+extern int g_last_gemm_pair;  // 1 if the last gemm_tc launch was the CTA-pair kernel
 cudaError_t gemm_any(int math, const GemmArgs &g, cudaStream_t stream, int *launches);
 cudaError_t column_sums(const float *a, int rows, int cols, int lda, float alpha, float *out, int accumulate,
                         float *partial, size_t partial_floats, cudaStream_t stream, int *launches);

@@ -22,11 +22,17 @@
 // weight-gradient GEMMs run on a side stream next to the persistent recurrent kernels, which pin
 // 80 SMs for milliseconds; CTAs that only become resident later find the queue drained and exit.
 #include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
 
 #include "rnn_common.cuh"
 #include "tc_common.cuh"
 
 namespace b200 {
+int g_gemm_pair = -1;
+int g_gemm_tma_store = 1;
+int g_last_gemm_pair = 0;
 namespace {
 
 using namespace tc;
@@ -57,6 +63,7 @@ struct TcParams {
   float *partial;
   int tiles_m, tiles_n, total;   // total = tiles_m * tiles_n * splits
   int *ticket;                   // [0] next tile, [1] CTAs finished (both self-resetting)
+  int tma_store;                 // CTA-pair kernel: the epilogue leaves through TMA tile stores (beta = 0, no split-K)
 };
 
 template <bool A_KMAJOR, bool B_KMAJOR, int TBN>
@@ -297,6 +304,369 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ===========================================================================
+// CTA-pair variant (tcgen05 cta_group::2): 256 x 256 tiles on two SMs of one TPC
+// ===========================================================================
+// The one-CTA kernel above stages 48 KB of fp32 operands per 2.1 MFLOP and is bound by L2 -> SM delivery
+// (10.4 TB/s measured, 41 % of the TF32 rate).  Here a cluster of two CTAs owns a 256 x 256 tile: each CTA
+// loads ITS 128 rows of A and ITS half (128 columns) of B -- 32 KB per 2.1 MFLOP and SM -- and the leader
+// CTA issues tcgen05.mma.cta_group::2 (M = 256), which reads both halves of B out of the two shared memories
+// and accumulates each CTA's 128 rows in that CTA's tensor memory.  Same roles as above:
+//   warp 0   leader: ticket scheduler (hands every tile to both CTAs) + TMA producer; peer: TMA producer
+//   warp 1   leader: MMA issuer (commits multicast to both CTAs' barriers); both: tensor-memory owner
+//   warps 2-9 epilogue of the CTA's own 128 rows
+// Barriers that gate the LEADER on work of both CTAs live in the leader and take remote arrivals from the
+// peer: full[] (TMA bytes of both CTAs, cp.async.bulk.tensor.cta_group::2), acc_empty[], q_empty[].
+// Epilogue: with one output row per lane and 16-byte stores, a warp store touches 32 different lines, and the
+// write path -- not the main loop -- bounds the kernel once the operands arrive faster (the K = 40 projection
+// needs 87 us just to write its 164 MB).  So the pair kernel's epilogue warps park each [32 rows x 32 columns]
+// block in shared memory (128-byte swizzle, conflict-free 16-byte stores) and hand it to a TMA tile store:
+// whole 128-byte lines leave the SM without touching the load/store unit (beta = 0 and no split-K only;
+// otherwise the register path of the one-CTA kernel).
+constexpr int kStages2 = 4;
+constexpr int kB2Bytes = 128 * TBK * 4;                 // this CTA's half of the 256-column B tile
+constexpr int kStage2Bytes = kABytes + kB2Bytes;        // 32 KB
+constexpr int kEpiStageBytes = 2 * 32 * 128;            // per epilogue warp: two [32 rows x 128 B] boxes for the TMA stores
+constexpr size_t kSmem2 = 1024 + (size_t)kStages2 * kStage2Bytes + (size_t)kEpiWarps * kEpiStageBytes + 512;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;          // shared::cluster address -> the even (leader) CTA of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acq_cluster(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// TMA load of a CTA pair: the bytes are counted on the LEADER CTA's barrier (same offset as `bar` here)
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all prior tcgen05.mma of this thread arrive on `bar` of BOTH CTAs of the pair when they complete
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, TcParams p) {
+  constexpr int TBN = 256, TBM2 = 256;
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint8_t *sA = smem;                           // [kStages2][16 KB]
+  uint8_t *sB = smem + kStages2 * kABytes;      // [kStages2][16 KB]
+  uint8_t *sE = smem + kStages2 * kStage2Bytes; // [kEpiWarps][2][32 rows x 128 B], 1024-byte aligned boxes
+  uint64_t *full = reinterpret_cast<uint64_t *>(sE + kEpiWarps * kEpiStageBytes);
+  uint64_t *empty = full + kStages2;
+  uint64_t *acc_full = empty + kStages2;     // [2]
+  uint64_t *acc_empty = acc_full + 2;        // [2]   (the leader's counts both CTAs' epilogue warps)
+  uint64_t *q_full = acc_empty + 2;          // [kQ]
+  uint64_t *q_empty = q_full + kQ;           // [kQ]  (the leader's counts both CTAs' consumers)
+  int *tile_q = reinterpret_cast<int *>(q_empty + kQ);  // [kQ]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tile_q + kQ);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int nkb = (p.K + TBK - 1) / TBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages2; s++) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(acc_full + b, 1);
+      mbar_init(acc_empty + b, 2 * kEpiWarps);
+    }
+    for (int q = 0; q < kQ; q++) {
+      mbar_init(q_full + q, 1);
+      mbar_init(q_empty + q, 2 * (1 + kEpiWarps));   // leader: MMA + epilogue warps; peer: producer + epilogue warps
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers exist before anyone arrives remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // the same objects in the leader CTA, as shared::cluster addresses
+  const uint32_t ld_acc_empty = mapa_u32(smem_u32(acc_empty), 0), ld_q_empty = mapa_u32(smem_u32(q_empty), 0);
+
+  auto decode = [&](int tile, int &m0, int &n0, int &z, int &kb0, int &kb1) {
+    const int tn = tile % p.tiles_n;
+    const int r = tile / p.tiles_n;
+    const int tm = r % p.tiles_m;
+    z = r / p.tiles_m;
+    m0 = tm * TBM2 + (int)rank * TBM;   // this CTA's 128 rows
+    n0 = tn * TBN;
+    kb0 = z * p.kb_per_split;
+    kb1 = min(nkb, kb0 + p.kb_per_split);
+  };
+
+  if (warp == 0) {
+    // ===== leader: tile scheduler; both: TMA producer =====
+    if (lane == 0) {
+      const uint32_t pr_q_full = mapa_u32(smem_u32(q_full), 1), pr_tile_q = mapa_u32(smem_u32(tile_q), 1);
+      uint32_t it = 0;
+      for (uint32_t qi = 0;; qi++) {
+        const uint32_t slot = qi % kQ;
+        int tile;
+        if (leader) {
+          tile = atomicAdd(p.ticket, 1);
+          if (tile >= p.total) tile = -1;
+          mbar_wait_acq_cluster(q_empty + slot, ((qi / kQ) & 1) ^ 1);
+          tile_q[slot] = tile;
+          asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(pr_tile_q + slot * 4), "r"(tile) : "memory");
+          mbar_arrive(q_full + slot);
+          mbar_arrive_cluster(pr_q_full + slot * 8);
+        } else {
+          mbar_wait_acq_cluster(q_full + slot, (qi / kQ) & 1);
+          tile = tile_q[slot];
+          mbar_arrive_cluster(ld_q_empty + slot * 8);
+        }
+        if (tile < 0) break;
+        int m0, n0, z, kb0, kb1;
+        decode(tile, m0, n0, z, kb0, kb1);
+        const int nh = n0 + (int)rank * 128;   // this CTA's half of the B tile
+        for (int kb = kb0; kb < kb1; kb++, it++) {
+          const uint32_t s = it % kStages2;
+          mbar_wait(empty + s, ((it / kStages2) & 1) ^ 1);
+          if (leader) mbar_expect_tx(full + s, 2 * kStage2Bytes);   // both CTAs' bytes land on this barrier
+          uint8_t *a = sA + s * kABytes, *b = sB + s * kB2Bytes;
+          if (A_KMAJOR) {
+            tma_load_2d_pair(a, &tmA, kb * TBK, m0, full + s);
+          } else {
+#pragma unroll
+            for (int j = 0; j < TBM / 32; j++) tma_load_2d_pair(a + j * (TBK * 128), &tmA, m0 + j * 32, kb * TBK, full + s);
+          }
+          if (B_KMAJOR) {
+            tma_load_2d_pair(b, &tmB, kb * TBK, nh, full + s);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 128 / 32; j++) tma_load_2d_pair(b + j * (TBK * 128), &tmB, nh + j * 32, kb * TBK, full + s);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== leader: MMA issuer =====
+    if (leader) {
+      constexpr uint32_t idesc = instr_desc(kFmtTF32, A_KMAJOR ? 0 : 1, B_KMAJOR ? 0 : 1, TBM2, TBN);
+      uint32_t it = 0, ai = 0;
+      for (uint32_t qi = 0;; qi++) {
+        mbar_wait(q_full + (qi % kQ), (qi / kQ) & 1);
+        const int tile = tile_q[qi % kQ];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(q_empty + (qi % kQ));
+        if (tile < 0) break;
+        int m0, n0, z, kb0, kb1;
+        decode(tile, m0, n0, z, kb0, kb1);
+        if (kb1 <= kb0) continue;  // empty split: the epilogue writes zeros
+        const uint32_t buf = ai & 1;
+        mbar_wait_acq_cluster(acc_empty + buf, ((ai >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * TBN;
+        for (int kb = kb0; kb < kb1; kb++, it++) {
+          const uint32_t s = it % kStages2;
+          mbar_wait(full + s, (it / kStages2) & 1);
+          tc_fence_after();
+          const uint32_t a = smem_u32(sA + s * kABytes), b = smem_u32(sB + s * kB2Bytes);
+#pragma unroll
+          for (int k = 0; k < TBK / 8; k++) {
+            const uint64_t ad = A_KMAJOR ? smem_desc(a + k * 32, 0, 1024, kLayoutSw128)
+                                         : smem_desc(a + k * 1024, TBK * 128, 512, kLayoutSw128Base32);
+            const uint64_t bd = B_KMAJOR ? smem_desc(b + k * 32, 0, 1024, kLayoutSw128)
+                                         : smem_desc(b + k * 1024, TBK * 128, 512, kLayoutSw128Base32);
+            if (elect_one()) mma_tf32_pair(acc, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          if (elect_one()) {
+            tc_commit_pair(empty + s);                          // frees the stage in both CTAs
+            if (kb == kb1 - 1) tc_commit_pair(acc_full + buf);  // accumulator complete, both CTAs
+          }
+          __syncwarp();
+        }
+        ai++;
+      }
+    }
+  } else {
+    // ===== epilogue of this CTA's 128 rows: TMEM -> registers -> global =====
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const bool direct = p.splits <= 1;
+    const int ldo = direct ? p.ldc : p.N;
+    uint32_t ai = 0, nst = 0;   // nst: blocks this warp has handed to TMA stores
+    for (uint32_t qi = 0;; qi++) {
+      mbar_wait_acq_cluster(q_full + (qi % kQ), (qi / kQ) & 1);
+      const int tile = tile_q[qi % kQ];
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(q_empty + (qi % kQ));
+        else mbar_arrive_cluster(ld_q_empty + (qi % kQ) * 8);
+      }
+      if (tile < 0) break;
+      int m0, n0, z, kb0, kb1;
+      decode(tile, m0, n0, z, kb0, kb1);
+      const bool have = kb1 > kb0;
+      const uint32_t buf = ai & 1;
+      if (have) {
+        mbar_wait(acc_full + buf, (ai >> 1) & 1);
+        tc_fence_after();
+      }
+      const int m = m0 + q * 32 + lane;
+      float *out = direct ? p.C : p.partial + (size_t)z * p.M * p.N;
+      const bool vec_ok = (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll 1
+      for (int c = half * (TBN / 64); c < (half + 1) * (TBN / 64); c++) {
+        const int nb0 = n0 + c * 32;
+        if (nb0 >= p.N) break;
+        uint32_t r[32];
+        if (have) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TBN + c * 32, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) r[j] = 0u;
+        }
+        if (p.tma_store) {
+          // ---- [32 rows x 32 columns] -> shared memory (row = lane, 16-byte chunk j at j ^ (row & 7)) -> TMA store
+          uint8_t *box = sE + (warp - 2) * kEpiStageBytes + (nst & 1) * (kEpiStageBytes / 2);
+          if (nst >= 2) {   // the store that last read this box (two chunks ago) must be done with it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j4 = 0; j4 < 8; j4++) {
+            const int n = nb0 + j4 * 4;
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              v[e] = p.alpha * __uint_as_float(r[j4 * 4 + e]);
+              if (p.bias_a && n + e < p.N) v[e] += p.bias_a[n + e];
+              if (p.bias_b && n + e < p.nb) v[e] += p.bias_b[n + e];
+            }
+            *reinterpret_cast<float4 *>(box + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+          fence_proxy_async();   // generic-proxy writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, box, nb0, m0 + q * 32);   // rows >= M and columns >= N are clipped by the TMA unit
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          nst++;
+        } else if (m < p.M) {
+          float *row = out + (size_t)m * ldo;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; j4++) {
+            const int n = nb0 + j4 * 4;
+            if (n >= p.N) break;
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) v[e] = p.alpha * __uint_as_float(r[j4 * 4 + e]);
+            if (vec_ok && n + 3 < p.N) {
+              if (direct) {
+                if (p.beta != 0.f) {
+                  const float4 o = *reinterpret_cast<const float4 *>(row + n);
+                  v[0] += p.beta * o.x; v[1] += p.beta * o.y; v[2] += p.beta * o.z; v[3] += p.beta * o.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                  if (p.bias_a) v[e] += p.bias_a[n + e];
+                  if (p.bias_b && n + e < p.nb) v[e] += p.bias_b[n + e];
+                }
+              }
+              *reinterpret_cast<float4 *>(row + n) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                if (n + e >= p.N) break;
+                float x = v[e];
+                if (direct) {
+                  if (p.beta != 0.f) x += p.beta * row[n + e];
+                  if (p.bias_a) x += p.bias_a[n + e];
+                  if (p.bias_b && n + e < p.nb) x += p.bias_b[n + e];
+                }
+                row[n + e] = x;
+              }
+            }
+          }
+        }
+      }
+      if (have) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {   // this warp's quarter of the buffer is drained: tell the leader's MMA issuer
+          if (leader) mbar_arrive(acc_empty + buf);
+          else mbar_arrive_cluster(ld_acc_empty + buf * 8);
+        }
+        ai++;
+      }
+    }
+    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores have landed
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's tensor memory is part of the pair's allocation: both CTAs are done with it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+  if (threadIdx.x == 0) {  // last CTA out re-arms the ticket for the next launch that uses this slot
+    __threadfence();
+    if (atomicAdd(p.ticket + 1, 1) == (int)gridDim.x - 1) {
+      p.ticket[0] = 0;
+      p.ticket[1] = 0;
+      __threadfence();
+    }
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -399,6 +769,29 @@ cudaError_t launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams 
   return cudaGetLastError();
 }
 
+template <bool AK, bool BK>
+cudaError_t launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tcm, const TcParams &p,
+                        cudaStream_t s) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_pair_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
+  const int pairs = std::min(p.total, sm_count() / 2);   // one cluster of two CTAs per TPC
+  tc_gemm_pair_kernel<AK, BK><<<2 * pairs, kThreads, kSmem2, s>>>(ta, tb, tcm, p);
+  return cudaGetLastError();
+}
+cudaError_t launch_pair_any(bool ak, bool bk, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tcm,
+                            const TcParams &p, cudaStream_t s) {
+  if (ak && bk) return launch_pair<true, true>(ta, tb, tcm, p, s);
+  if (ak) return launch_pair<true, false>(ta, tb, tcm, p, s);
+  if (bk) return launch_pair<false, true>(ta, tb, tcm, p, s);
+  return launch_pair<false, false>(ta, tb, tcm, p, s);
+}
+
 template <int TBN>
 cudaError_t launch_any(bool ak, bool bk, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p,
                        cudaStream_t s) {
@@ -446,11 +839,19 @@ cudaError_t gemm_tc(const GemmArgs &g, cudaStream_t stream, int *launches) {
       }
     }
   }
+  if (g_gemm_pair > 0 && g.N > 128) {   // test hook: the CTA-pair kernel wherever its tile shape exists
+    tbn = 256;
+    splits = 1;
+  }
+  // CTA pairs (256 x 256 tiles, each SM stages 32 instead of 48 KB per k-block) for the big products: the hoisted
+  // projection and the input gradient of a layer.  Not for the short-and-wide split-K weight gradients (they run
+  // on the side stream next to a recurrent kernel that pins 80 SMs, where whole TPCs are rarely free).
+  const bool pair = g_gemm_pair != 0 && tbn == 256 && splits == 1 && (g_gemm_pair > 0 || g.M >= 2048);
   CUtensorMap ta, tb;
   const CUtensorMapSwizzle kmaj = CU_TENSOR_MAP_SWIZZLE_128B, mnmaj = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   bool ok = ak ? make_map(&ta, g.A, g.K, g.M, g.sam, TBK, TBM, kmaj)
                : make_map(&ta, g.A, g.M, g.K, g.sak, 32, TBK, mnmaj);
-  ok = ok && (bk ? make_map(&tb, g.B, g.K, g.N, g.sbn, TBK, tbn, kmaj)
+  ok = ok && (bk ? make_map(&tb, g.B, g.K, g.N, g.sbn, TBK, pair ? 128 : tbn, kmaj)
                  : make_map(&tb, g.B, g.N, g.K, g.sbk, 32, TBK, mnmaj));
   if (!ok) return cudaErrorNotSupported;
 
@@ -460,12 +861,19 @@ cudaError_t gemm_tc(const GemmArgs &g, cudaStream_t stream, int *launches) {
   p.kb_per_split = (nkb + splits - 1) / splits;
   p.splits = splits;
   p.partial = g.partial;
-  p.tiles_m = (g.M + TBM - 1) / TBM;
+  p.tiles_m = pair ? (g.M + 2 * TBM - 1) / (2 * TBM) : (g.M + TBM - 1) / TBM;
   p.tiles_n = (g.N + tbn - 1) / tbn;
   p.total = p.tiles_m * p.tiles_n * splits;
   p.ticket = ticket_slot();
   if (!p.ticket) return cudaErrorMemoryAllocation;
-  cudaError_t e = tbn == 256 ? launch_any<256>(ak, bk, ta, tb, p, stream) : launch_any<128>(ak, bk, ta, tb, p, stream);
+  g_last_gemm_pair = pair ? 1 : 0;
+  CUtensorMap tcm;
+  memset(&tcm, 0, sizeof(tcm));
+  // output through TMA tile stores ([32 rows x 32 columns] boxes, 128-byte swizzle) when nothing has to be read back
+  p.tma_store = (pair && g.beta == 0.f && g_gemm_tma_store != 0 &&
+                 make_map(&tcm, g.C, g.N, g.M, g.ldc, 32, 32, kmaj)) ? 1 : 0;
+  cudaError_t e = pair ? launch_pair_any(ak, bk, ta, tb, tcm, p, stream)
+                       : (tbn == 256 ? launch_any<256>(ak, bk, ta, tb, p, stream) : launch_any<128>(ak, bk, ta, tb, p, stream));
   if (e != cudaSuccess) return e;
   if (launches) (*launches)++;
   if (splits > 1) {

@@ -311,6 +311,14 @@ def gemm(torch, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bi
                              _stream(torch, C.device)), "b200rnnGemm")
 
 
+def set_tuning(key, value):
+    """Test / tuning hook (include/b200rnn.h b200rnnSetTuning), e.g. ("GEMM_PAIR", -1 | 0 | 1)."""
+    L = lib()
+    L.b200rnnSetTuning.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    if L.b200rnnSetTuning(key.encode(), int(value)) != 0:
+        raise KeyError(key)
+
+
 def column_sums(torch, a, out, accumulate, workspace, alpha=1.0):
     rows, cols = a.shape
     _check(lib().b200rnnColumnSums(a.data_ptr(), rows, cols, a.stride(0), alpha, out.data_ptr(), int(accumulate),
