@@ -323,10 +323,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // block in shared memory (128-byte swizzle, conflict-free 16-byte stores) and hand it to a TMA tile store:
 // whole 128-byte lines leave the SM without touching the load/store unit (beta = 0 and no split-K only;
 // otherwise the register path of the one-CTA kernel).
-constexpr int kStages2 = 4;
+#ifndef B200_GEMM2_STAGES
+#define B200_GEMM2_STAGES 6
+#endif
+#ifndef B200_GEMM2_EPIBUFS
+#define B200_GEMM2_EPIBUFS 1
+#endif
+constexpr int kStages2 = B200_GEMM2_STAGES;
+constexpr int kEpiBufs = B200_GEMM2_EPIBUFS;            // boxes per epilogue warp for the TMA stores
 constexpr int kB2Bytes = 128 * TBK * 4;                 // this CTA's half of the 256-column B tile
 constexpr int kStage2Bytes = kABytes + kB2Bytes;        // 32 KB
-constexpr int kEpiStageBytes = 2 * 32 * 128;            // per epilogue warp: two [32 rows x 128 B] boxes for the TMA stores
+constexpr int kEpiStageBytes = kEpiBufs * 32 * 128;     // per epilogue warp: [32 rows x 128 B] boxes for the TMA stores
 constexpr size_t kSmem2 = 1024 + (size_t)kStages2 * kStage2Bytes + (size_t)kEpiWarps * kEpiStageBytes + 512;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;          // shared::cluster address -> the even (leader) CTA of the pair
 
@@ -576,9 +583,9 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (p.tma_store) {
           // ---- [32 rows x 32 columns] -> shared memory (row = lane, 16-byte chunk j at j ^ (row & 7)) -> TMA store
-          uint8_t *box = sE + (warp - 2) * kEpiStageBytes + (nst & 1) * (kEpiStageBytes / 2);
-          if (nst >= 2) {   // the store that last read this box (two chunks ago) must be done with it
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          uint8_t *box = sE + (warp - 2) * kEpiStageBytes + (nst % kEpiBufs) * 4096;
+          if (nst >= kEpiBufs) {   // the store that last read this box must be done with it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kEpiBufs - 1) : "memory");
             __syncwarp();
           }
 #pragma unroll
