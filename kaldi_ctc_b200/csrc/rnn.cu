@@ -448,17 +448,21 @@ b200rnnStatus_t b200rnnBackwardData(b200rnnPlan_t p, int T, const float *y, cons
     }
     p->launches++;
     if (dxl) {
-      for (int d = 0; d < p->dirs; d++) {
-        const PseudoLayer &q = p->pl[l * p->dirs + d];
-        GemmArgs g = {};
-        g.M = TB; g.N = din; g.K = p->GH; g.alpha = 1.f; g.beta = d == 0 ? 0.f : 1.f;
-        g.A = rs + p->r_gates[d][l]; g.sam = p->GH; g.sak = 1;
-        g.B = w + q.w_in; g.sbk = din; g.sbn = 1;
-        g.C = dxl; g.ldc = din;
-        g.splits = 1;
-        Timed tm(p, 2, stream);
-        CK(gemm_any(p->math, g, stream, &p->launches));
+      // dx = sum over directions of dG_d . Wi_d: both products in ONE pass over dx where the GEMM can
+      // (gemm_any falls back to two launches, the second accumulating)
+      const PseudoLayer &q0 = p->pl[l * p->dirs];
+      GemmArgs g = {};
+      g.M = TB; g.N = din; g.K = p->GH; g.alpha = 1.f; g.beta = 0.f;
+      g.A = rs + p->r_gates[0][l]; g.sam = p->GH; g.sak = 1;
+      g.B = w + q0.w_in; g.sbk = din; g.sbn = 1;
+      g.C = dxl; g.ldc = din;
+      g.splits = 1;
+      if (p->dirs == 2) {
+        g.A2 = rs + p->r_gates[1][l];
+        g.B2 = w + p->pl[l * p->dirs + 1].w_in;
       }
+      Timed tm(p, 2, stream);
+      CK(gemm_any(p->math, g, stream, &p->launches));
     }
   }
   return B200RNN_STATUS_SUCCESS;

@@ -40,6 +40,9 @@ struct GemmArgs {
   int nb;
   int splits;
   float *partial;
+  // optional second operand pair of the same shape and strides: C = alpha * (A.B + A2.B2) + beta * C + bias
+  // (the input gradient of a bidirectional layer: one product per direction, one pass over C)
+  const float *A2, *B2;
 };
 cudaError_t gemm_fp32(const GemmArgs &g, cudaStream_t stream, int *launches);
 // C = beta*C + bias + sum_z partial[z]  (fixed summation order)

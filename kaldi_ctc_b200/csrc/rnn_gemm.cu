@@ -183,6 +183,26 @@ int g_last_gemm_tc = 0;
 
 cudaError_t gemm_any(int math, const GemmArgs &g, cudaStream_t stream, int *launches) {
   g_last_gemm_tc = 0;
+  if (g.A2 && g.B2) {
+    // two products into one C: in one launch where the CTA-pair kernel applies, else one after the other
+    if (math == 1) {
+      cudaError_t e = gemm_tc(g, stream, launches);
+      if (e != cudaErrorNotSupported) {
+        g_last_gemm_tc = 1;
+        return e;
+      }
+      cudaGetLastError();
+    }
+    GemmArgs g1 = g;
+    g1.A2 = g1.B2 = nullptr;
+    cudaError_t e = gemm_any(math, g1, stream, launches);
+    if (e != cudaSuccess) return e;
+    g1.A = g.A2;
+    g1.B = g.B2;
+    g1.beta = 1.f;
+    g1.bias_a = g1.bias_b = nullptr;
+    return gemm_any(math, g1, stream, launches);
+  }
   if (math == 1) {
     cudaError_t e = gemm_tc(g, stream, launches);
     if (e != cudaErrorNotSupported) {

@@ -64,6 +64,7 @@ struct TcParams {
   int tiles_m, tiles_n, total;   // total = tiles_m * tiles_n * splits
   int *ticket;                   // [0] next tile, [1] CTAs finished (both self-resetting)
   int tma_store;                 // CTA-pair kernel: the epilogue leaves through TMA tile stores (beta = 0, no split-K)
+  int nkb_total, nkb1;           // CTA-pair kernel: k-blocks in all / of the first operand pair (A, B); the rest come from (A2, B2)
 };
 
 template <bool A_KMAJOR, bool B_KMAJOR, int TBN>
@@ -394,6 +395,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void 
 template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                     const __grid_constant__ CUtensorMap tmC, TcParams p) {
   constexpr int TBN = 256, TBM2 = 256;
   extern __shared__ uint8_t smem_dyn[];
@@ -413,11 +415,15 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int nkb = (p.K + TBK - 1) / TBK;
+  const int nkb = p.nkb_total;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.nkb1 < p.nkb_total) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
     for (int s = 0; s < kStages2; s++) {
       mbar_init(full + s, 1);
       mbar_init(empty + s, 1);
@@ -457,6 +463,10 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     kb1 = min(nkb, kb0 + p.kb_per_split);
   };
 
+  // Width of a column tile: MN-major B is staged in 32-column boxes, so the last tile of a row only loads and
+  // multiplies the 64-column groups that exist (N = 640: tiles of 256, 256, 128 instead of three full ones).
+  auto tile_width = [&](int n0) { return B_KMAJOR ? TBN : min(TBN, ((p.N - n0 + 63) >> 6) << 6); };
+
   if (warp == 0) {
     // ===== leader: tile scheduler; both: TMA producer =====
     if (lane == 0) {
@@ -481,23 +491,26 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (tile < 0) break;
         int m0, n0, z, kb0, kb1;
         decode(tile, m0, n0, z, kb0, kb1);
-        const int nh = n0 + (int)rank * 128;   // this CTA's half of the B tile
-        for (int kb = kb0; kb < kb1; kb++, it++) {
+        const int nw = tile_width(n0), nwh = nw >> 1;   // tile width; this CTA stages half of it
+        const int nh = n0 + (int)rank * nwh;
+        for (int kbt = kb0; kbt < kb1; kbt++, it++) {
+          const bool second = kbt >= p.nkb1;             // k-blocks of the second operand pair follow the first's
+          const CUtensorMap *ma = second ? &tmA2 : &tmA, *mb = second ? &tmB2 : &tmB;
+          const int kb = second ? kbt - p.nkb1 : kbt;
           const uint32_t s = it % kStages2;
           mbar_wait(empty + s, ((it / kStages2) & 1) ^ 1);
-          if (leader) mbar_expect_tx(full + s, 2 * kStage2Bytes);   // both CTAs' bytes land on this barrier
+          if (leader) mbar_expect_tx(full + s, 2 * (kABytes + nwh * TBK * 4));   // both CTAs' bytes land on this barrier
           uint8_t *a = sA + s * kABytes, *b = sB + s * kB2Bytes;
           if (A_KMAJOR) {
-            tma_load_2d_pair(a, &tmA, kb * TBK, m0, full + s);
+            tma_load_2d_pair(a, ma, kb * TBK, m0, full + s);
           } else {
 #pragma unroll
-            for (int j = 0; j < TBM / 32; j++) tma_load_2d_pair(a + j * (TBK * 128), &tmA, m0 + j * 32, kb * TBK, full + s);
+            for (int j = 0; j < TBM / 32; j++) tma_load_2d_pair(a + j * (TBK * 128), ma, m0 + j * 32, kb * TBK, full + s);
           }
           if (B_KMAJOR) {
-            tma_load_2d_pair(b, &tmB, kb * TBK, nh, full + s);
+            tma_load_2d_pair(b, mb, kb * TBK, nh, full + s);
           } else {
-#pragma unroll
-            for (int j = 0; j < 128 / 32; j++) tma_load_2d_pair(b + j * (TBK * 128), &tmB, nh + j * 32, kb * TBK, full + s);
+            for (int j = 0; j < nwh / 32; j++) tma_load_2d_pair(b + j * (TBK * 128), mb, nh + j * 32, kb * TBK, full + s);
           }
         }
       }
@@ -505,7 +518,7 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ===== leader: MMA issuer =====
     if (leader) {
-      constexpr uint32_t idesc = instr_desc(kFmtTF32, A_KMAJOR ? 0 : 1, B_KMAJOR ? 0 : 1, TBM2, TBN);
+      constexpr uint32_t idesc0 = instr_desc(kFmtTF32, A_KMAJOR ? 0 : 1, B_KMAJOR ? 0 : 1, TBM2, 0);
       uint32_t it = 0, ai = 0;
       for (uint32_t qi = 0;; qi++) {
         mbar_wait(q_full + (qi % kQ), (qi / kQ) & 1);
@@ -516,6 +529,7 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int m0, n0, z, kb0, kb1;
         decode(tile, m0, n0, z, kb0, kb1);
         if (kb1 <= kb0) continue;  // empty split: the epilogue writes zeros
+        const uint32_t idesc = idesc0 | ((uint32_t)(tile_width(n0) >> 3) << 17);   // N of this tile
         const uint32_t buf = ai & 1;
         mbar_wait_acq_cluster(acc_empty + buf, ((ai >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -777,8 +791,8 @@ cudaError_t launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams 
 }
 
 template <bool AK, bool BK>
-cudaError_t launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tcm, const TcParams &p,
-                        cudaStream_t s) {
+cudaError_t launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &ta2, const CUtensorMap &tb2,
+                        const CUtensorMap &tcm, const TcParams &p, cudaStream_t s) {
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -788,15 +802,15 @@ cudaError_t launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUte
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   const int pairs = std::min(p.total, sm_count() / 2);   // one cluster of two CTAs per TPC
-  tc_gemm_pair_kernel<AK, BK><<<2 * pairs, kThreads, kSmem2, s>>>(ta, tb, tcm, p);
+  tc_gemm_pair_kernel<AK, BK><<<2 * pairs, kThreads, kSmem2, s>>>(ta, tb, ta2, tb2, tcm, p);
   return cudaGetLastError();
 }
-cudaError_t launch_pair_any(bool ak, bool bk, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tcm,
-                            const TcParams &p, cudaStream_t s) {
-  if (ak && bk) return launch_pair<true, true>(ta, tb, tcm, p, s);
-  if (ak) return launch_pair<true, false>(ta, tb, tcm, p, s);
-  if (bk) return launch_pair<false, true>(ta, tb, tcm, p, s);
-  return launch_pair<false, false>(ta, tb, tcm, p, s);
+cudaError_t launch_pair_any(bool ak, bool bk, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &ta2,
+                            const CUtensorMap &tb2, const CUtensorMap &tcm, const TcParams &p, cudaStream_t s) {
+  if (ak && bk) return launch_pair<true, true>(ta, tb, ta2, tb2, tcm, p, s);
+  if (ak) return launch_pair<true, false>(ta, tb, ta2, tb2, tcm, p, s);
+  if (bk) return launch_pair<false, true>(ta, tb, ta2, tb2, tcm, p, s);
+  return launch_pair<false, false>(ta, tb, ta2, tb2, tcm, p, s);
 }
 
 template <int TBN>
@@ -861,11 +875,22 @@ cudaError_t gemm_tc(const GemmArgs &g, cudaStream_t stream, int *launches) {
   ok = ok && (bk ? make_map(&tb, g.B, g.K, g.N, g.sbn, TBK, pair ? 128 : tbn, kmaj)
                  : make_map(&tb, g.B, g.N, g.K, g.sbk, 32, TBK, mnmaj));
   if (!ok) return cudaErrorNotSupported;
+  // second operand pair (same shape and strides): only the CTA-pair kernel walks both in one launch
+  const bool dual = g.A2 != nullptr && g.B2 != nullptr;
+  if (dual && !pair) return cudaErrorNotSupported;
+  CUtensorMap ta2 = ta, tb2 = tb;
+  if (dual) {
+    ok = ak ? make_map(&ta2, g.A2, g.K, g.M, g.sam, TBK, TBM, kmaj) : make_map(&ta2, g.A2, g.M, g.K, g.sak, 32, TBK, mnmaj);
+    ok = ok && (bk ? make_map(&tb2, g.B2, g.K, g.N, g.sbn, TBK, 128, kmaj) : make_map(&tb2, g.B2, g.N, g.K, g.sbk, 32, TBK, mnmaj));
+    if (!ok) return cudaErrorNotSupported;
+  }
 
   TcParams p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.alpha = g.alpha; p.beta = g.beta;
   p.C = g.C; p.ldc = g.ldc; p.bias_a = g.bias_a; p.bias_b = g.bias_b; p.nb = g.nb;
-  p.kb_per_split = (nkb + splits - 1) / splits;
+  p.nkb1 = nkb;
+  p.nkb_total = dual ? 2 * nkb : nkb;
+  p.kb_per_split = pair ? p.nkb_total : (nkb + splits - 1) / splits;   // (the CTA-pair kernel never splits K)
   p.splits = splits;
   p.partial = g.partial;
   p.tiles_m = pair ? (g.M + 2 * TBM - 1) / (2 * TBM) : (g.M + TBM - 1) / TBM;
@@ -879,7 +904,7 @@ cudaError_t gemm_tc(const GemmArgs &g, cudaStream_t stream, int *launches) {
   // output through TMA tile stores ([32 rows x 32 columns] boxes, 128-byte swizzle) when nothing has to be read back
   p.tma_store = (pair && g.beta == 0.f && g_gemm_tma_store != 0 &&
                  make_map(&tcm, g.C, g.N, g.M, g.ldc, 32, 32, kmaj)) ? 1 : 0;
-  cudaError_t e = pair ? launch_pair_any(ak, bk, ta, tb, tcm, p, stream)
+  cudaError_t e = pair ? launch_pair_any(ak, bk, ta, tb, ta2, tb2, tcm, p, stream)
                        : (tbn == 256 ? launch_any<256>(ak, bk, ta, tb, p, stream) : launch_any<128>(ak, bk, ta, tb, p, stream));
   if (e != cudaSuccess) return e;
   if (launches) (*launches)++;

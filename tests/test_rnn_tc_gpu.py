@@ -108,6 +108,30 @@ def test_tensor_mode_within_stated_tolerance(mode, D, H, B, Tn):
     assert e_dx < 1e-2 and e_dw < 1e-2
 
 
+@pytest.mark.parametrize("mode,D,H,B,Tn,force", [(2, 640, 320, 16, 12, 1), (3, 640, 320, 16, 9, 1), (2, 136, 64, 7, 10, 1),
+                                                (2, 640, 320, 16, 130, -1)])
+def test_input_gradient_through_the_cta_pair_gemm(mode, D, H, B, Tn, force):
+    """dx = dG_fwd . Wi_fwd + dG_bwd . Wi_bwd in ONE launch of the CTA-pair GEMM (second operand pair, tiles of 256 /
+    256 / 128 columns at D = 640): forced at small sizes (GEMM_PAIR = 1), and chosen by the library itself at
+    T * B >= 2048 rows (the last case)."""
+    from kaldi_ctc_b200 import rnn
+    from oracle import pyoracle
+    rng = np.random.default_rng(mode * 10 + D + Tn)
+    n = pyoracle.rnn_param_count(mode, True, 1, D, H)
+    w = (rng.standard_normal(n) * 0.05).astype(np.float32)
+    x = rng.standard_normal((Tn * B, D)).astype(np.float32)
+    dy = rng.standard_normal((Tn * B, 2 * H)).astype(np.float32)
+    yr, dxr, dwr = pyoracle.rnn(mode, True, 1, H, x, w, B, dy=dy, dtype=np.float64)
+    rnn.set_tuning("GEMM_PAIR", force)
+    try:
+        y, dx, dw = _run_tc(mode, D, H, B, Tn, x, w, dy)
+    finally:
+        rnn.set_tuning("GEMM_PAIR", -1)
+    assert np.abs(y - yr).max() < 5e-3
+    assert np.abs(dx - dxr).max() / np.abs(dxr).max() < 1e-2
+    assert np.abs(dw - dwr).max() / np.abs(dwr).max() < 1e-2
+
+
 @pytest.mark.parametrize("mode,H,B,bc", [(2, 64, 23, 16), (3, 128, 23, 16), (2, 320, 50, 16), (3, 64, 13, 8),
                                          (1, 64, 21, 16)])
 def test_split_epilogue_chunks(monkeypatch, mode, H, B, bc):
