@@ -634,6 +634,7 @@ struct RingCfg {
   int pshift;            // log2(P)
   long long vrow_base;   // meta[b_lo].vrow0
   long long vrows;       // valid rows of this group
+  long long zrows;       // rows of this group that only need zeros: padded frames, every frame of an infeasible utterance
 };
 struct RowCur {
   int b, t, T, L, pitch, nstr;
@@ -685,6 +686,9 @@ __global__ void __launch_bounds__(kRingThreads, 2) ctc_grad_ring_kernel(CtcDev d
   int *s_us = reinterpret_cast<int *>(gam0 + 2 * rc.pitch_max);    // [pitch_max + 4]
   int *s_pos = s_us + rc.pitch_max + 4;                            // [pitch_max]
   int *s_ul = s_pos + rc.pitch_max;                                // [pitch_max]
+  // one row of zeros: the producer stores it over the padded rows BETWEEN the gradient rows, so that these writes
+  // ride along with the read-heavy main phase instead of forming a write-only tail (3 GB at configs[4])
+  float *zrow = reinterpret_cast<float *>(rsm + (((size_t)(reinterpret_cast<unsigned char *>(s_ul + rc.pitch_max) - rsm) + 127) & ~(size_t)127));
 
   const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
   const int A = d.A, b_end = d.b_lo + d.nb, pshift = rc.pshift;
@@ -697,6 +701,8 @@ __global__ void __launch_bounds__(kRingThreads, 2) ctc_grad_ring_kernel(CtcDev d
     for (int i = 0; i < rc.NA + rc.NT; i++) mbar_init(done_act + i, kRingConsumers / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int k = tid; k < (A >> 2); k += kRingThreads) reinterpret_cast<float4 *>(zrow)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zeros -> visible to the bulk stores
   __syncthreads();
 
   // first row of this CTA: the utterance that holds valid row v_lo
@@ -714,7 +720,36 @@ __global__ void __launch_bounds__(kRingThreads, 2) ctc_grad_ring_kernel(CtcDev d
 
   if (wi == kRingConsumers / 32) {
     // ===================== producer: one thread keeps both rings full and drains finished rows =====
-    if (lane == 0 && nrows > 0) {
+    if (lane == 0) {
+      // ---- this CTA's share of the zero rows: (zb, zt) walks the padded frames t in [T_b, Tmax) of feasible
+      //      utterances and every frame of infeasible ones, in utterance order
+      const long long z_lo = rc.zrows * blockIdx.x / gridDim.x, z_hi = rc.zrows * (blockIdx.x + 1) / gridDim.x;
+      long long zleft = z_hi - z_lo;
+      int zb = d.b_lo, zt = 0;
+      if (zleft > 0) {
+        long long skip = z_lo;
+        for (; zb < b_end; zb++) {
+          const UttMeta um = d.meta[zb];
+          const int first = um.feasible ? um.T : 0;
+          const long long cnt = d.Tmax - first;
+          if (skip < cnt) {
+            zt = first + (int)skip;
+            break;
+          }
+          skip -= cnt;
+        }
+      }
+      auto store_zero_row = [&]() {   // (joins the bulk group of the caller's next commit)
+        bulk_store(d.grad + ((long long)zt * d.B + zb) * A, zrow, (uint32_t)A * 4u);
+        zleft--;
+        if (++zt >= d.Tmax && zleft > 0) {
+          for (zb++; zb < b_end; zb++) {
+            const UttMeta um = d.meta[zb];
+            zt = um.feasible ? um.T : 0;
+            if (zt < d.Tmax) break;
+          }
+        }
+      };
       RowCur pa = cur, pt = cur, ps = cur;  // next activation row / next table row to request / next row to store
       auto issue_act = [&](int i) {
         uint64_t *bar = full_act + (i % rc.NA);
@@ -746,12 +781,22 @@ __global__ void __launch_bounds__(kRingThreads, 2) ctc_grad_ring_kernel(CtcDev d
         mbar_wait(done_act + (i % rc.NA), (uint32_t)(i / rc.NA) & 1u);  // row i finished in its slot
         bulk_store(d.grad + ((long long)ps.t * d.B + ps.b) * A, act_base + (size_t)(i % rc.NA) * rc.act_bytes,
                    (uint32_t)A * 4u);
+        if (zleft > 0) store_zero_row();   // same bulk group: the slot accounting below is unchanged
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         cur_next(d, ps, b_end, pshift);
         // the slot of row i-1 (its store was committed one row ago) takes row i+NA-1
         asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         if (i + rc.NA - 1 < nrows) issue_act(i + rc.NA - 1);
       }
+      // zero rows that outnumber this CTA's gradient rows (heavily padded batches)
+      for (int n = 0; zleft > 0; n++) {
+        store_zero_row();
+        if ((n & 7) == 7) {
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
+        }
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
   } else {
@@ -861,17 +906,6 @@ __global__ void __launch_bounds__(kRingThreads, 2) ctc_grad_ring_kernel(CtcDev d
     }
   }
 
-  // ---- zero rows: padded frames and infeasible utterances of this group
-  if (wi < kRingConsumers / 32) {
-    const long long rows = (long long)d.Tmax * d.nb;
-    for (long long lrow = (long long)blockIdx.x * 8 + wi; lrow < rows; lrow += (long long)gridDim.x * 8) {
-      const int t = (int)(lrow / d.nb), b = d.b_lo + (int)(lrow - (long long)t * d.nb);
-      const int Tb = d.meta[b].T, feas = d.meta[b].feasible;
-      if (t < Tb && feas) continue;
-      float4 *g4 = reinterpret_cast<float4 *>(d.grad + ((long long)t * d.B + b) * A);
-      for (int k = lane; k < (A >> 2); k += 32) g4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
 }
 
 // ===========================================================================
@@ -1201,10 +1235,10 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   rc.tab_bytes = (int)align_up((size_t)7 * p.pitch_max * 4, 128);
   rc.pitch_max = p.pitch_max;
   rc.pshift = P == 1 ? 0 : (P == 2 ? 1 : 2);
-  rc.vrow_base = rc.vrows = 0;
+  rc.vrow_base = rc.vrows = rc.zrows = 0;
   auto ring_bytes = [&]() {
     return (size_t)512 + (size_t)rc.NA * rc.act_bytes + (size_t)rc.NT * rc.tab_bytes +
-           sizeof(float) * ((size_t)5 * p.pitch_max + 8);
+           sizeof(float) * ((size_t)5 * p.pitch_max + 8) + 128 + (size_t)rc.act_bytes;   // (+ the row of zeros)
   };
   // two CTAs per SM (16 consumer warps keep the issue slots busy): <= ~113 KB each
   bool use_ring = grad && (A & 3) == 0 && A >= 1024 && (size_t)p.Tmax * B * A >= ((size_t)64 << 20);
@@ -1302,6 +1336,7 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
     if (grad && use_ring) {
       rc.vrow_base = p.meta[dev.b_lo].vrow0;
       rc.vrows = (dev.b_lo + dev.nb < B ? p.meta[dev.b_lo + dev.nb].vrow0 : vrows_total) - rc.vrow_base;
+      rc.zrows = rows - rc.vrows;
       const unsigned g3 = (unsigned)std::max<long long>(1, std::min<long long>(2 * num_sms, (rows + 7) / 8));
       ctc_grad_ring_kernel<<<g3, kRingThreads, ring_smem, stream>>>(dev, rc);
       if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
