@@ -8,7 +8,11 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-from kaldi_ctc_b200 import rnn  # noqa: E402
+from kaldi_ctc_b200 import rnn, _lib  # noqa: E402
+
+if os.environ.get("B200RNN_LIB"):   # tuning builds
+    import ctypes
+    _lib._cache["libb200rnn.so"] = ctypes.CDLL(os.path.abspath(os.environ["B200RNN_LIB"]))
 
 math = sys.argv[1] if len(sys.argv) > 1 else "tensor"
 T, B, D, H, mode = [int(v) for v in (sys.argv[2:7] + ["2000", "16", "640", "320", "2"][len(sys.argv) - 2:])]
