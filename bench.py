@@ -269,8 +269,12 @@ def gemm_roofline(dev, pk, pk_src):
     gp = measured_gemm_peaks(dev)
     bf16_burst = pk.get("bf16_tflops", pk.get("bf16_tflops_sustained"))
     peak = gp["tf32"]
-    traffic, src = ncu_traffic("tc_gemm")
-    return {"kernel": "tc_gemm_kernel (x.Wi^T, %dx%dx%d, fp32 operands in HBM)" % (M, N, K), "bound": "tensor", "achieved": ach,
+    traffic, src = ncu_traffic("tc_gemm_pair")
+    if traffic is None:
+        traffic, src = ncu_traffic("tc_gemm")
+    pair = int(rnn.lib().b200rnnLastGemmUsedCtaPair())
+    return {"kernel": "%s (x.Wi^T, %dx%dx%d, fp32 operands in HBM)" % ("tc_gemm_pair_kernel" if pair else "tc_gemm_kernel", M, N, K),
+            "bound": "tensor", "achieved": ach,
             "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "us_per_launch": ms * 1e3,
             "peak_source": "measured in this run: cuBLAS TF32 8192^3 best of 10",
             "measured_peaks_TFLOPs": {"cublas_tf32_8192": gp["tf32"], "cublas_bf16_8192": gp["bf16"],
@@ -425,7 +429,7 @@ def run_b200(args, rank, local_rank, world):
     cat_ms = [sum(p[k][0] for p in prof) for k in range(4)]
     cat_n = [sum(p[k][1] for p in prof) for k in range(4)]
     names = ["recurrent_forward (rec_tc_fwd_kernel)", "recurrent_backward (rec_tc_bwd_kernel)",
-             "projection + dx GEMMs (tc_gemm_kernel, main stream)",
+             "projection + dx GEMMs (tc_gemm_pair_kernel, main stream)",
              "weight-gradient GEMMs (tc_gemm_kernel, side stream: elapsed times overlap the recurrent kernels)"]
     # dominant kernel = the largest of the kernels on the step's critical path (the side-stream GEMMs hide under the
     # recurrent kernels; the ncu launch list under profiles/ gives the same ranking from serialised durations)
