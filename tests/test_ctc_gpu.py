@@ -132,6 +132,60 @@ def test_label_length_edges(ctx, L, T, A):
     _check(costs, grad, c_ref, g_ref)
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_random_ragged_batches_against_oracle(ctx, seed):
+    """Seeded random batches that stress the alpha/beta frame loop: tiny alphabets (many repeated labels), label
+    strings as long as the frames allow (tight alignments: every state on the edge of the reachable cone carries the
+    path), long T with short L (the forward-tilted lattice that broke the rejected shared-exponent variant), peaky
+    logits, every pairs-per-thread variant forced in turn (B200CTC_P hook), T not a multiple of the 8-frame block."""
+    from oracle import pyoracle
+    ctc = ctx[1]
+    rng = np.random.default_rng(9000 + seed)
+    B = int(rng.integers(1, 7))
+    A = int(rng.choice([2, 3, 5, 12, 48, 130]))
+    kind = seed % 4
+    il, labs = [], []
+    for b in range(B):
+        if kind == 0:      # tight: L + repeats == T or T - 1
+            L = int(rng.integers(1, 60))
+            lab = rng.integers(1, A, size=L)
+            rep = int((lab[1:] == lab[:-1]).sum())
+            T = L + rep + int(rng.integers(0, 2))
+        elif kind == 1:    # long T, short L
+            L = int(rng.integers(0, 6))
+            lab = rng.integers(1, A, size=L)
+            T = int(rng.integers(300, 900))
+        elif kind == 2:    # many repeats, medium
+            L = int(rng.integers(20, 200))
+            lab = rng.integers(1, min(A, 3), size=L) if A > 2 else np.ones(L, np.int64)
+            T = L + int((lab[1:] == lab[:-1]).sum()) + int(rng.integers(0, 300))
+        else:              # general
+            L = int(rng.integers(1, 300))
+            lab = rng.integers(1, A, size=L)
+            T = L + int((lab[1:] == lab[:-1]).sum()) + int(rng.integers(1, 500))
+        il.append(T)
+        labs.append(lab.astype(np.int32))
+    il = np.array(il, np.int32)
+    ll = np.array([len(l) for l in labs], np.int32)
+    fl = np.concatenate(labs) if ll.sum() else np.zeros(0, np.int32)
+    Tm = int(il.max())
+    scale = 6.0 if seed % 3 == 0 else 2.0   # peaky / ordinary logits
+    act = (rng.standard_normal((Tm, B, A)) * scale).astype(np.float32)
+    for b in range(B):
+        act[il[b]:, b, :] = 0
+    c_ref, g_ref = pyoracle.ctc(act, fl, ll, il, dtype=np.float64)
+    try:
+        for P in (0, 2, 4):
+            ctc.set_tuning("P", P)
+            costs, grad = _run(ctx, act, fl, ll, il)
+            np.testing.assert_allclose(costs, c_ref, rtol=LOSS_RTOL, atol=1e-5)
+            assert np.abs(grad - g_ref).max() < GRAD_ATOL, "P=%d kind=%d" % (P, kind)
+            for b in range(B):
+                assert np.abs(grad[il[b]:, b]).max(initial=0) == 0
+    finally:
+        ctc.set_tuning("P", 0)
+
+
 def test_alphabet_not_multiple_of_four_and_nonzero_blank(ctx):
     from oracle import pyoracle
     rng = np.random.default_rng(2)
