@@ -96,6 +96,39 @@ def test_cta_pair_kernel_every_operand_major(tA, tB, M, N, K, tma_store):
     assert (err <= 2e-3 * bound + 1e-4).all(), "max err %g" % err.max()
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_cta_pair_kernel_random_shapes(seed):
+    """Seeded random shapes through the forced CTA-pair kernel: M from below one CTA's 128 rows to several 256-row
+    tiles, N from 132 to 900 (column tiles of every width the MN-major path produces: 64, 128, 192, 256), K from one
+    partial k-block to many, alpha / bias present or not."""
+    import torch
+    from kaldi_ctc_b200 import rnn
+    rng = np.random.default_rng(500 + seed)
+    tA, tB = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+    M = int(rng.integers(1, 1200)) * (4 if tA else 1)     # MN-major A needs a row pitch of whole 16-byte chunks
+    N = int(rng.integers(33, 226)) * 4
+    K = int(rng.integers(1, 300)) * 4
+    alpha = float(rng.choice([1.0, -0.75]))
+    A = rng.standard_normal((K, M) if tA else (M, K)).astype(np.float32)
+    Bm = rng.standard_normal((N, K) if tB else (K, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32) if seed % 2 else None
+    opA, opB = (A.T if tA else A).astype(np.float64), (Bm.T if tB else Bm).astype(np.float64)
+    want = alpha * (opA @ opB) + (bias if bias is not None else 0.0)
+    bound = abs(alpha) * (np.abs(opA) @ np.abs(opB))
+    At, Bt = torch.from_numpy(A).cuda(), torch.from_numpy(Bm).cuda()
+    bt = torch.from_numpy(bias).cuda() if bias is not None else None
+    Ct = torch.full((M, N), -3.0, device="cuda")
+    rnn.set_tuning("GEMM_PAIR", 1)
+    try:
+        rnn.gemm(torch, tA, tB, M, N, K, alpha, At, A.shape[1], Bt, Bm.shape[1], 0.0, Ct, N, bias=bt, math=rnn.MATH_TENSOR)
+        torch.cuda.synchronize()
+        assert rnn.lib().b200rnnLastGemmUsedCtaPair() == 1
+    finally:
+        rnn.set_tuning("GEMM_PAIR", -1)
+    err = np.abs(Ct.cpu().numpy() - want)
+    assert (err <= 2e-3 * bound + 1e-4).all(), "tA=%d tB=%d M=%d N=%d K=%d max err %g" % (tA, tB, M, N, K, err.max())
+
+
 def test_unaligned_operands_fall_back_to_fp32():
     import torch
     from kaldi_ctc_b200 import rnn
