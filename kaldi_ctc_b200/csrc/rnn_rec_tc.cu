@@ -577,7 +577,7 @@ rec_tc_bwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
     mbar_init(rfull + 0, 1);
     mbar_init(rfull + 1, 1);
     for (int m = 0; m < 4; m++) mbar_init(acc_full + m, 1);  // committed by the warp that issued the tile
-    mbar_init(dg_ready, 128 * EH);
+    mbar_init(dg_ready, 128 * EH);   // (kept for the layout; the hand-off itself uses named barrier 4)
     fence_barrier_init();
     mbar_expect_tx(rfull + 0, r_bytes);
     mbar_expect_tx(rfull + 1, r_bytes);
@@ -630,7 +630,8 @@ rec_tc_bwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
     long long qm[3] = {0, 0, 0};
     for (int step = 0; step + 1 < T; step++) {
       const long long n0 = profm ? clock64() : 0;
-      mbar_wait(dg_ready, step & 1);
+      // (a named barrier, not the mbarrier: warps sleeping in mbarrier.try_wait resume later -- measured 0.735 -> 0.723 us per step)
+      asm volatile("bar.sync 4, %0;" ::"n"(32 * kIssuers + 128 * EH) : "memory");
       const long long n1 = profm ? clock64() : 0;
       tc_fence_after();
       for (int m = warp; m < MT; m += kIssuers) {
@@ -857,7 +858,7 @@ rec_tc_bwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
           *reinterpret_cast<uint2 *>(dgs + off) = v;
         }
         fence_proxy_async();  // my generic smem writes -> visible to the tensor core (async proxy)
-        mbar_arrive(dg_ready);
+        asm volatile("bar.arrive 4, %0;" ::"n"(32 * kIssuers + 128 * EH) : "memory");   // gate gradients of this step are in the B tile
       }
       const long long c4 = prof ? clock64() : 0;
       // ---- off the critical path: gradients to HBM, operands of the next step
@@ -929,7 +930,7 @@ rec_tc_bwd_kernel(RecArgs a, const __grid_constant__ RecMaps tm) {
         }
         tc_fence_before();
         if (prof) pe[6] += clock64() - c6;
-        // every epilogue thread has arrived on dg_ready (the MMAs above needed it), i.e. is past its reads of
+        // every epilogue thread has arrived on the gate-gradient barrier (the MMAs above needed it), i.e. is past its reads of
         // this step's ring slot: refill it
         if (kBulk && step + kRB < T) issue_ops(step + kRB);
       }
