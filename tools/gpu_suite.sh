@@ -19,10 +19,10 @@ timeout 250 ncu --set full --clock-control none --import-source on -k regex:rec_
 timeout 250 ncu --set full --clock-control none --import-source on -k regex:rec_tc_bwd -s 5 -c 1 -o gpurun_out/${TAG}_prof_recbwd -f \
     python bench.py --steps 2 --warmup 1 $NOX > gpurun_out/${TAG}_ncu_recbwd.log 2>&1; echo "ncu rec bwd rc=$?"
 timeout 100 python tools/gemm_pair_time.py > gpurun_out/${TAG}_gemm_pair_time.log 2>&1; echo "gemm time rc=$?"
-timeout 250 ncu --set full --clock-control none --import-source on -k regex:tc_gemm_pair -s 40 -c 1 -o gpurun_out/${TAG}_prof_gemm -f \
+timeout 250 ncu --set full --clock-control none --import-source on -k regex:tc_gemm_pair -s 5 -c 1 -o gpurun_out/${TAG}_prof_gemm -f \
     python tools/gemm_pair_time.py > gpurun_out/${TAG}_ncu_gemm.log 2>&1; echo "ncu gemm rc=$?"
 timeout 60 python tools/ctc_stress_time.py 32 2 > gpurun_out/${TAG}_ctc32.log 2>&1; echo "ctc32 rc=$?"
-timeout 250 ncu --set full --clock-control none --import-source on -k regex:ctc_ -s 6 -c 3 -o gpurun_out/${TAG}_prof_ctc -f \
+timeout 250 ncu --set full --clock-control none --import-source on -k regex:ctc_ -s 6 -c 6 -o gpurun_out/${TAG}_prof_ctc -f \
     python tools/ctc_stress_time.py 32 2 > gpurun_out/${TAG}_ncu_ctc.log 2>&1; echo "ncu ctc rc=$?"
 B200CTC_PROFILE=1 timeout 100 python tools/ctc_roofline.py 256 2>&1 | grep b200ctc | tail -1 > gpurun_out/${TAG}_ctc_per_kernel.log
 timeout 100 python tools/ctc_time.py 1 4 > gpurun_out/${TAG}_ctc_small.log 2>&1
