@@ -79,6 +79,7 @@ struct CtcDev {
   const int *uniq_start;  // per utt: nuniq+1 offsets into pos
   const int *pos;         // per utt: label positions grouped by label
   const int *nuniq;       // [B] number of distinct labels (uploaded with the CSR, after K1/K2 are queued)
+  const int *order;       // [B] K2: CTA i of a group works on utterance order[b_lo + i] (longest first)
   float *lse2;            // [Tmax*B] base-2 log-sum-exp of each row
   float *E;
   float *alpha;
@@ -448,23 +449,25 @@ __device__ __forceinline__ void ctc_ab_run(const CtcDev &d, const UttMeta &um, i
   }
 }
 
+// One CTA per (utterance, direction): alpha and beta share nothing, and as separate CTAs two of them fit an SM
+// (registers, ~79 KB of stages), so the kernel's end is not tied to the one SM that holds the longest utterance's
+// 20 warps.  CTA i of a group works on utterance order[b_lo + i/2] (longest first), direction i % 2.
 template <int P>
-__global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int frames_per_stage, int stage_floats) {
+__global__ void __launch_bounds__(512, 2) ctc_alpha_beta_kernel(CtcDev d, int frames_per_stage, int stage_floats) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);               // [2][kStages]
-  float2 *bnd = reinterpret_cast<float2 *>(smem_raw + 64);               // [2][2][32] (value, offset)
-  float *fin = reinterpret_cast<float *>(smem_raw + 64 + 1024);          // [2][4]
-  float *stages = reinterpret_cast<float *>(smem_raw + 2048);            // [2][kStages][stage_floats]
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);               // [kStages]
+  float2 *bnd = reinterpret_cast<float2 *>(smem_raw + 64);               // [2][32] (value, offset)
+  float *fin = reinterpret_cast<float *>(smem_raw + 64 + 1024);          // [4]
+  float *stages = reinterpret_cast<float *>(smem_raw + 2048);            // [kStages][stage_floats]
 
-  const int b = d.b_lo + blockIdx.x;
+  const int role = blockIdx.x & 1;
+  const int b = d.order[d.b_lo + (blockIdx.x >> 1)];
   const UttMeta um = d.meta[b];
   if (!um.feasible) return;
-  const int NT = blockDim.x >> 1;
-  const int role = threadIdx.x >= NT ? 1 : 0;
-  const int r = threadIdx.x - role * NT;
+  const int r = threadIdx.x;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2 * kStages; i++) mbar_init(mbar + i, 1);
+    for (int i = 0; i < kStages; i++) mbar_init(mbar + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -475,16 +478,12 @@ __global__ void __launch_bounds__(1024, 1) ctc_alpha_beta_kernel(CtcDev d, int f
   const int nbar = nwarps_active * 32;
   // FULL: every pair of every lane of this warp lies inside the lattice and has a label state (i < L)
   const bool full = ((r >> 5) + 1) * 32 * P <= um.L;
-  uint64_t *bar = mbar + role * kStages;
-  float *stg = stages + (size_t)role * kStages * stage_floats;
-  float2 *bn = bnd + role * 64;
-  float *fn = fin + role * 4;
   if (role == 0) {
-    if (full) ctc_ab_run<P, 0, true>(d, um, b, r, nthreads_needed, nbar, bar, stg, stage_floats, bn, fn, frames_per_stage);
-    else ctc_ab_run<P, 0, false>(d, um, b, r, nthreads_needed, nbar, bar, stg, stage_floats, bn, fn, frames_per_stage);
+    if (full) ctc_ab_run<P, 0, true>(d, um, b, r, nthreads_needed, nbar, mbar, stages, stage_floats, bnd, fin, frames_per_stage);
+    else ctc_ab_run<P, 0, false>(d, um, b, r, nthreads_needed, nbar, mbar, stages, stage_floats, bnd, fin, frames_per_stage);
   } else {
-    if (full) ctc_ab_run<P, 1, true>(d, um, b, r, nthreads_needed, nbar, bar, stg, stage_floats, bn, fn, frames_per_stage);
-    else ctc_ab_run<P, 1, false>(d, um, b, r, nthreads_needed, nbar, bar, stg, stage_floats, bn, fn, frames_per_stage);
+    if (full) ctc_ab_run<P, 1, true>(d, um, b, r, nthreads_needed, nbar, mbar, stages, stage_floats, bnd, fin, frames_per_stage);
+    else ctc_ab_run<P, 1, false>(d, um, b, r, nthreads_needed, nbar, mbar, stages, stage_floats, bnd, fin, frames_per_stage);
   }
 }
 
@@ -914,7 +913,7 @@ __global__ void __launch_bounds__(kRingThreads, 2) ctc_grad_ring_kernel(CtcDev d
 struct Plan {
   int A, B, Tmax, maxL, pitch_max;
   long long sumT, sumL;
-  size_t off_meta, off_labels, off_uniq_lab, off_uniq_start, off_pos, off_nuniq;  // header block
+  size_t off_meta, off_labels, off_order, off_uniq_lab, off_uniq_start, off_pos, off_nuniq;  // header block
   size_t header_bytes;
   size_t off_lse2, off_E, off_alpha, off_beta, off_offA, off_offB, off_logp2, off_costs, off_flags;
   size_t total;
@@ -957,6 +956,7 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int A,
   size_t o = 0;
   p->off_meta = o;        o = align_up(o + sizeof(UttMeta) * B, 256);
   p->off_labels = o;      o = align_up(o + sizeof(int) * (p->sumL + 1), 256);
+  p->off_order = o;       o = align_up(o + sizeof(int) * B, 256);   // (meta, labels, order: what K1 / K2 need)
   p->off_uniq_lab = o;    o = align_up(o + sizeof(int) * (p->sumL + 1), 256);
   p->off_uniq_start = o;  o = align_up(o + sizeof(int) * (p->sumL + B + 1), 256);
   p->off_pos = o;         o = align_up(o + sizeof(int) * (p->sumL + 1), 256);
@@ -1061,7 +1061,7 @@ bool ensure_pinned(Staging &s, size_t bytes, size_t ncosts) {
 
 template <int P>
 cudaError_t launch_k2(const CtcDev &dev, int B, int NT, int F, int stage_floats, cudaStream_t stream, DeviceState *ds) {
-  const size_t smem = 2048 + sizeof(float) * 2 * kStages * (size_t)stage_floats;
+  const size_t smem = 2048 + sizeof(float) * kStages * (size_t)stage_floats;
   size_t &granted = ds->k2_smem[P == 1 ? 0 : (P == 2 ? 1 : 2)];
   if (smem > granted) {
     cudaError_t e = cudaFuncSetAttribute(ctc_alpha_beta_kernel<P>,
@@ -1069,7 +1069,7 @@ cudaError_t launch_k2(const CtcDev &dev, int B, int NT, int F, int stage_floats,
     if (e != cudaSuccess) return e;
     granted = smem;
   }
-  ctc_alpha_beta_kernel<P><<<dev.nb, 2 * NT, smem, stream>>>(dev, F, stage_floats);
+  ctc_alpha_beta_kernel<P><<<2 * dev.nb, NT, smem, stream>>>(dev, F, stage_floats);
   return cudaGetLastError();
 }
 
@@ -1093,6 +1093,19 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   Staging &g_stage = ds->stage;
   const Tuning tune = tuning();
   if (!ensure_pinned(g_stage, p.header_bytes, (size_t)B)) return CTC_STATUS_MEMOPS_FAILED;
+  // tuning aid: B200CTC_PROFILE=1 serialises the groups and prints the duration of each kernel
+  const int prof_mode = tune.profile;
+  const bool prof = prof_mode == 1;
+  const bool timeline = prof_mode == 2;   // keeps the groups; prints each kernel's start/end on its own stream
+  // (only worth it when the row kernels are long: a slab of >= 256 MB)
+  const bool big = (size_t)p.Tmax * B * A >= ((size_t)64 << 20);
+  // Utterance groups on separate streams: the latency-bound alpha/beta recursion of one group runs
+  // under the bandwidth-bound row kernels of the others (only the first K2 and the last K3 stay exposed).
+  const int env_groups = tune.groups;
+  int ngroups = B >= 16 ? 2 : 1;   // measured at B=256, A=4000: 1 -> 10.47 ms, 2 -> 9.95, 4 -> 9.91, 8 -> 9.99
+  if (!big) ngroups = 1;
+  if (env_groups >= 1 && env_groups <= kMaxGroups) ngroups = std::min(env_groups, B);
+  if (prof || tune.one_stream) ngroups = 1;
   unsigned char *h = g_stage.pinned;
   UttMeta *hm = reinterpret_cast<UttMeta *>(h + p.off_meta);
   int *hl = reinterpret_cast<int *>(h + p.off_labels);
@@ -1124,6 +1137,20 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
     m.vrow0 = vrows_total;
     if (m.feasible) vrows_total += m.T;
     hm[b] = m;
+  }
+  // K2 runs one CTA per utterance and its CTAs differ 20-fold in work (frames x lattice states): inside every
+  // utterance group they are handed out longest first, so that the long recursions start at once and the short
+  // ones fill the SMs behind them (256 utterances on 148 SMs in input order: the kernel ended 1.6x later than its
+  // longest CTA needs)
+  {
+    int *ho = reinterpret_cast<int *>(h + p.off_order);
+    for (int gi = 0; gi < ngroups; gi++) {
+      const int lo = (int)((long long)B * gi / ngroups), hi = (int)((long long)B * (gi + 1) / ngroups);
+      for (int b = lo; b < hi; b++) ho[b] = b;
+      std::stable_sort(ho + lo, ho + hi, [&](int x, int y) {
+        return (long long)p.meta[x].T * (p.meta[x].L + 1) > (long long)p.meta[y].T * (p.meta[y].L + 1);
+      });
+    }
   }
   unsigned char *w = static_cast<unsigned char *>(workspace);
   if (cudaMemcpyAsync(w, h, p.off_uniq_lab, cudaMemcpyHostToDevice, stream) != cudaSuccess)
@@ -1188,6 +1215,7 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   dev.uniq_start = reinterpret_cast<const int *>(w + p.off_uniq_start);
   dev.pos = reinterpret_cast<const int *>(w + p.off_pos);
   dev.nuniq = reinterpret_cast<const int *>(w + p.off_nuniq);
+  dev.order = reinterpret_cast<const int *>(w + p.off_order);
   dev.lse2 = reinterpret_cast<float *>(w + p.off_lse2);
   dev.E = reinterpret_cast<float *>(w + p.off_E);
   dev.alpha = reinterpret_cast<float *>(w + p.off_alpha);
@@ -1210,7 +1238,7 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
   // alpha/beta recursion of one group runs under the bandwidth-bound row kernels of the other.
   const int NT = (int)align_up((size_t)(npairs + P - 1) / P, 32);
   // emission stages of K2: 8 frames each when that fits (a stage then holds one re-centring block), a power of
-  // two in any case; 2 directions x kStages stages, at most ~192 KB of shared memory (one CTA per SM anyway)
+  // two in any case; kStages stages per CTA (one direction of one utterance), at most 96 KB: two CTAs per SM
   const int stage_floats = std::min(std::max(kStageFloats, kRenorm * p.pitch_max), 6144);
   int F = 1;
   while (F < 32 && 2 * F * p.pitch_max <= stage_floats) F *= 2;
@@ -1256,19 +1284,6 @@ ctcStatus_t run(const float *act, float *grad, const int *flat_labels, const int
       ring_set = ring_smem;
     }
   }
-  // tuning aid: B200CTC_PROFILE=1 serialises the groups and prints the duration of each kernel
-  const int prof_mode = tune.profile;
-  const bool prof = prof_mode == 1;
-  const bool timeline = prof_mode == 2;   // keeps the groups; prints each kernel's start/end on its own stream
-  // (only worth it when the row kernels are long: a slab of >= 256 MB)
-  const bool big = (size_t)p.Tmax * B * A >= ((size_t)64 << 20);
-  // Utterance groups on separate streams: the latency-bound alpha/beta recursion of one group runs
-  // under the bandwidth-bound row kernels of the others (only the first K2 and the last K3 stay exposed).
-  const int env_groups = tune.groups;
-  int ngroups = B >= 16 ? 2 : 1;   // measured at B=256, A=4000: 1 -> 10.47 ms, 2 -> 9.95, 4 -> 9.91, 8 -> 9.99
-  if (!big) ngroups = 1;
-  if (env_groups >= 1 && env_groups <= kMaxGroups) ngroups = std::min(env_groups, B);
-  if (prof || tune.one_stream) ngroups = 1;
   // Several groups: the row kernels (K1, K3) of all groups run back to back on the caller's stream; each
   // group's alpha/beta kernel runs on its own HIGH-PRIORITY stream between them, so its CTAs are placed as
   // soon as the group's K1 is done instead of queueing behind the row kernels of the other groups.
