@@ -317,7 +317,9 @@ class NnetCtcUpdater:
             red.submit_max(self.nonfinite_dev)   # a bad minibatch on ANY rank skips the update on EVERY rank
             d = self.affine.Backprop(top_in, self.deriv[:rows], None, in_deriv=self.dact[0][:rows],
                                      grad_out=(self.gW, self.gb))
-            red.submit([self.gW, self.gb], lambda: self.affine.Update(self.gW, self.gb))
+            # (queued only: this runs on the main stream, which must not wait for a transfer; the first recurrent
+            #  component's submission, on the side stream, applies it)
+            red.submit([self.gW, self.gb], lambda: self.affine.Update(self.gW, self.gb), drain=False)
         else:
             d = self.affine.Backprop(top_in, self.deriv[:rows], self.affine if update else None,
                                      in_deriv=self.dact[0][:rows])

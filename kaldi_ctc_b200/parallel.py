@@ -19,15 +19,29 @@ def shard_utterances(num_utts, world, rank):
 class GradientReducer:
     """Issues one asynchronous all-reduce(sum) per gradient tensor as soon as it exists and applies
     the caller's update when the reduction has landed (top layer first, so the transfers overlap the
-    lower layers' backward)."""
+    lower layers' backward).  Updates lag their reduction by ONE submission: when the next component's
+    gradient is submitted (a recurrent layer later, i.e. long after the previous transfer has finished),
+    the previous components' reductions are waited for and their updates applied -- only the last
+    component's reduction and update are left for finish(), instead of every update of the step."""
 
     def __init__(self, group=None):
         self.group = group
         self.pending = []
 
-    def submit(self, tensors, on_done):
+    def _drain(self, entries):
+        for works, on_done in entries:
+            for w in works:
+                w.wait()
+            on_done()
+
+    def submit(self, tensors, on_done, drain=True):
+        """drain=False: only queue (for a caller that is on a stream which must not wait for transfers)."""
         works = [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True) for t in tensors]
-        self.pending.append((works, on_done))
+        if not drain:
+            self.pending.append((works, on_done))
+            return
+        older, self.pending = self.pending, [(works, on_done)]
+        self._drain(older)   # (after the new transfer has been issued: it starts while the older updates run)
 
     def submit_max(self, flag):
         """all-reduce(max) of a small flag tensor, ahead of the gradients on the same communicator."""
@@ -35,11 +49,8 @@ class GradientReducer:
                              lambda: None))
 
     def finish(self):
-        for works, on_done in self.pending:
-            for w in works:
-                w.wait()
-            on_done()
-        self.pending = []
+        older, self.pending = self.pending, []
+        self._drain(older)
 
 
 def reduce_scalar_sum(value, device="cpu"):
