@@ -9,12 +9,13 @@
 //        row (one HBM read of the activations), and a gather of the emission
 //        log-probabilities of the utterance's own lattice symbols (blank + its
 //        L labels) into a compact per-utterance table E[t][u], base-2 logs.
-//   K2 ctc_alpha_beta<P>     one CTA per utterance.  Two warp groups run the
-//        alpha (forward) and beta (backward) recursions CONCURRENTLY over the
-//        blank-interleaved lattice, P (blank,label) state pairs per thread,
+//   K2 ctc_alpha_beta<P>     one CTA per (utterance, direction), the longest
+//        utterances first: the alpha (forward) and beta (backward) recursions
+//        over the blank-interleaved lattice run CONCURRENTLY in separate CTAs,
+//        P (blank,label) state pairs per thread,
 //        neighbour states by warp shuffle (+ one smem word per warp boundary),
 //        emissions staged into shared memory by TMA bulk copies
-//        (cp.async.bulk + mbarrier, 4-stage ring per direction).  Log-space,
+//        (cp.async.bulk + mbarrier, 4-stage ring).  Log-space,
 //        base 2.  Every thread keeps its states relative to its OWN integer
 //        offset, re-centred every kRenorm frames without any block-wide
 //        reduction, so the stored values stay within ~+-100 and fp32 keeps
@@ -257,7 +258,7 @@ ctc_rowstats_gather_kernel(CtcDev d) {
 // ===========================================================================
 // Pair i (0..L) = {Y_i: a blank state, X_i: the label state after it (alpha) /
 // before it (beta)}.  With the label string reversed, beta obeys the SAME
-// recurrence as alpha, so both warp groups run this code:
+// recurrence as alpha, so both directions run this code:
 //   Y_i <- Eb   + lse(Y_i, X_{i-1})
 //   X_i <- El_i + lse(X_i, Y_i, skip_i ? X_{i-1} : 0)
 // alpha: Y_i = state 2i, X_i = state 2i+1, time ascending, label i.
